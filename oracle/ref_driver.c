@@ -14,7 +14,7 @@
  *   --time N    : times N calls of Lk(NULL,tree) (both_sides as given) and prints one JSON line
  *                 (the "reference" CPU baseline of bench.py).
  *
- * usage: ref_driver [--dump FILE] [--time N] [--both_sides 0|1] [--dlk N_EDGES] -- <phyml args>
+ * usage: ref_driver [--dump FILE] [--time N] [--warmup W] [--both_sides 0|1] [--dlk N_EDGES] -- <phyml args>
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -208,7 +208,7 @@ static void dump_all(t_tree *tree, int n_dlk_edges)
 int main(int argc, char **argv)
 {
   const char *dump_file = NULL;
-  int n_time = 0, both_sides = 0, n_dlk = 4;
+  int n_time = 0, n_warm = 0, both_sides = 0, n_dlk = 4;
   int i, split = -1;
   option *io;
   calign *cdata;
@@ -226,6 +226,8 @@ int main(int argc, char **argv)
       dump_file = argv[++i];
     else if (!strcmp(argv[i], "--time") && i + 1 < argc)
       n_time = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "--warmup") && i + 1 < argc)
+      n_warm = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--both_sides") && i + 1 < argc)
       both_sides = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--dlk") && i + 1 < argc)
@@ -285,6 +287,7 @@ int main(int argc, char **argv)
   {
     double *t = (double *)malloc(sizeof(double) * n_time);
     double tot = 0.0, best = 1e300;
+    for (i = 0; i < n_warm; ++i) Lk(NULL, tree);
     for (i = 0; i < n_time; ++i)
     {
       double t0 = now_s();

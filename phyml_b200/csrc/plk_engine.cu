@@ -1,0 +1,1011 @@
+// phyml_b200/csrc/plk_engine.cu -- instance management, launch scheduling and the C ABI
+// (include/phyml_b200.h) of the B200 likelihood engine.  No CPU fallback: every entry point runs
+// CUDA kernels on the instance's stream or fails with PLK_ERR_CUDA.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/phyml_b200.h"
+#include "plk_kernels.cuh"
+
+using namespace plk;
+
+namespace
+{
+std::string g_create_error;
+
+struct NcclApi
+{
+  void *handle = nullptr;
+  struct UniqueId
+  {
+    char internal[128];
+  };
+  int (*GetUniqueId)(UniqueId *) = nullptr;
+  int (*CommInitRank)(void **, int, UniqueId, int) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  bool load(std::string &err)
+  {
+    if (handle) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names)
+    {
+      handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (handle) break;
+    }
+    if (!handle)
+    {
+      err = std::string("cannot dlopen libnccl.so.2: ") + dlerror();
+      return false;
+    }
+    GetUniqueId = (decltype(GetUniqueId))dlsym(handle, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(handle, "ncclCommInitRank");
+    AllReduce = (decltype(AllReduce))dlsym(handle, "ncclAllReduce");
+    CommDestroy = (decltype(CommDestroy))dlsym(handle, "ncclCommDestroy");
+    GetErrorString = (decltype(GetErrorString))dlsym(handle, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy)
+    {
+      err = "libnccl is missing required symbols";
+      return false;
+    }
+    return true;
+  }
+};
+NcclApi g_nccl;
+
+constexpr int    kStageSlots = 8;
+constexpr size_t kStageBytes = 256 * 1024;
+constexpr int    kMaxReduceBlocks = 4096;
+}  // namespace
+
+struct plk_instance
+{
+  plk_config   cfg{};
+  cudaStream_t stream = nullptr;
+  std::string  err;
+  int          apply_scaling = 1;
+  int          num_sms = 148;
+
+  double   *d_wght = nullptr;
+  short    *d_invar = nullptr;
+  uint32_t *d_tipmask = nullptr;
+  uint8_t  *d_tipcodes = nullptr;
+  size_t    tip_stride = 0;
+  ModelDev *d_model = nullptr;
+  double   *d_pmat = nullptr;
+  size_t    pmat_elems = 0;   // ncatg*ns*ns doubles of P
+  size_t    pmat_stride = 0;  // per-handle record: P followed (ns == 4) by the tip table TP[cat][16][4]
+
+  std::vector<double *> clv;
+  std::vector<int *>    scale;
+
+  double *d_site_lnl = nullptr, *d_site_lk = nullptr, *d_site_lk_cat = nullptr;
+  int    *d_fact = nullptr;
+  double *d_dot_prod = nullptr;
+  double *d_partials = nullptr;
+  int    *d_warn = nullptr;
+  double *d_result = nullptr;
+
+  ResultHost        *h_result = nullptr;
+  ResultHost        *h_result_dev = nullptr;
+  unsigned long long seq = 0;
+
+  // pinned staging ring for small descriptor uploads
+  char       *h_stage[kStageSlots] = {};
+  cudaEvent_t stage_ev[kStageSlots] = {};
+  int         stage_next = 0;
+  char       *d_stage = nullptr;  // device mirror, one region per slot
+
+  std::vector<double>                   tip_table;  // [n_codes][ns]
+  std::vector<uint32_t>                 masks;
+  std::unordered_map<uint32_t, int>     mask_to_code;
+  bool                                  eigen_ready = false;
+  bool                                  site_valid = false;
+
+  long long launches = 0;
+  size_t    bytes = 0;
+
+  void *comm = nullptr;
+  bool  allreduce = false;
+  int   rank = 0, world = 1;
+  double l_min = 1e-8, l_max = 100.0;  // host copy of mod->l_min / l_max (plk_set_model)
+  int    trav_umax = 2;                // items per thread of the fused traversal kernel
+  int    trav_blocks_per_sm = 2;
+
+  // scheduling scratch
+  std::vector<int> lvl_write, lvl_read, op_level;
+};
+
+#define CU_TRY(inst, call)                                                                         \
+  do                                                                                               \
+  {                                                                                                \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+    {                                                                                              \
+      (inst)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                            \
+      return PLK_ERR_CUDA;                                                                         \
+    }                                                                                              \
+  } while (0)
+
+#define ARG_CHECK(inst, cond, msg) \
+  do                               \
+  {                                \
+    if (!(cond))                   \
+    {                              \
+      (inst)->err = (msg);         \
+      return PLK_ERR_ARG;          \
+    }                              \
+  } while (0)
+
+namespace
+{
+template <typename T>
+int dev_alloc(plk_instance *inst, T **p, size_t n)
+{
+  const size_t b = std::max<size_t>(n * sizeof(T), 256);
+  CU_TRY(inst, cudaMalloc((void **)p, b));
+  inst->bytes += b;
+  return PLK_OK;
+}
+
+size_t clv_elems(const plk_instance *inst)
+{
+  return (size_t)inst->cfg.n_patterns * inst->cfg.ncatg * inst->cfg.ns;
+}
+
+int ensure_clv(plk_instance *inst, int h)
+{
+  if (inst->clv[h]) return PLK_OK;
+  int rc = dev_alloc(inst, &inst->clv[h], clv_elems(inst) + 4);
+  if (rc) return rc;
+  rc = dev_alloc(inst, &inst->scale[h], (size_t)inst->cfg.n_patterns);
+  if (rc) return rc;
+  // zero-weight patterns are never written by K1 (avx.c:515-520): start from defined contents
+  CU_TRY(inst, cudaMemsetAsync(inst->clv[h], 0, clv_elems(inst) * sizeof(double), inst->stream));
+  CU_TRY(inst, cudaMemsetAsync(inst->scale[h], 0, (size_t)inst->cfg.n_patterns * sizeof(int), inst->stream));
+  return PLK_OK;
+}
+
+// copy a small host block to the device through the pinned ring; returns the device address
+int stage_upload(plk_instance *inst, const void *src, size_t bytes, void **dev_out)
+{
+  if (bytes > kStageBytes)
+  {
+    inst->err = "internal: staging block too large";
+    return PLK_ERR_ARG;
+  }
+  const int s = inst->stage_next;
+  inst->stage_next = (s + 1) % kStageSlots;
+  CU_TRY(inst, cudaEventSynchronize(inst->stage_ev[s]));
+  memcpy(inst->h_stage[s], src, bytes);
+  char *dst = inst->d_stage + (size_t)s * kStageBytes;
+  CU_TRY(inst, cudaMemcpyAsync(dst, inst->h_stage[s], bytes, cudaMemcpyHostToDevice, inst->stream));
+  CU_TRY(inst, cudaEventRecord(inst->stage_ev[s], inst->stream));
+  *dev_out = dst;
+  return PLK_OK;
+}
+
+int check_side(plk_instance *inst, const plk_side &s, bool need_data)
+{
+  const bool tip = s.tip >= 0;
+  const bool in = s.clv >= 0;
+  ARG_CHECK(inst, tip != in, "operand must be exactly one of tip / clv");
+  if (tip) ARG_CHECK(inst, s.tip < inst->cfg.n_tips, "tip index out of range");
+  if (in)
+  {
+    ARG_CHECK(inst, s.clv < inst->cfg.n_clv, "clv handle out of range");
+    if (need_data) ARG_CHECK(inst, inst->clv[s.clv] != nullptr, "clv handle read before it was ever written");
+  }
+  return PLK_OK;
+}
+
+SideDev side_dev(plk_instance *inst, const plk_side &s)
+{
+  SideDev d;
+  if (s.tip >= 0)
+  {
+    d.clv = nullptr;
+    d.scale = nullptr;
+    d.tip = inst->d_tipcodes + (size_t)s.tip * inst->tip_stride;
+  }
+  else
+  {
+    d.clv = inst->clv[s.clv];
+    d.scale = inst->scale[s.clv];
+    d.tip = nullptr;
+  }
+  return d;
+}
+
+int reduce_grid(const plk_instance *inst, int threads)
+{
+  const int need = (inst->cfg.n_patterns + threads - 1) / threads;
+  return std::max(1, std::min(need, std::min(kMaxReduceBlocks, inst->num_sms * 16)));
+}
+
+// finish a reduction: second stage, optional all-reduce, publish, wait
+int finish_reduction(plk_instance *inst, int nblocks, int nv, double *out0, double *out1, int *warn)
+{
+  const unsigned long long seq = ++inst->seq;
+  const int                publish = inst->allreduce ? 0 : 1;
+  k_reduce_final<<<1, 256, 0, inst->stream>>>(inst->d_partials, nblocks, nv, inst->d_result, inst->d_warn,
+                                              inst->h_result_dev, seq, publish);
+  inst->launches++;
+  CU_TRY(inst, cudaGetLastError());
+  if (inst->allreduce)
+  {
+    // the warning flag travels as a third double so that one sum all-reduce carries everything
+    const int rc = g_nccl.AllReduce(inst->d_result, inst->d_result, 3, /*ncclDouble*/ 8, /*ncclSum*/ 0, inst->comm,
+                                    inst->stream);
+    if (rc != 0)
+    {
+      inst->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+      return PLK_ERR_NCCL;
+    }
+    k_publish<<<1, 1, 0, inst->stream>>>(inst->d_result, inst->h_result_dev, seq);
+    inst->launches++;
+    CU_TRY(inst, cudaGetLastError());
+  }
+  // spin on the mapped result; fall back to the stream status to catch launch failures
+  volatile ResultHost *h = inst->h_result;
+  unsigned long long   spins = 0;
+  while (h->seq != seq)
+  {
+    if ((++spins & 0x3fff) == 0)
+    {
+      cudaError_t q = cudaStreamQuery(inst->stream);
+      if (q == cudaSuccess)
+      {
+        if (h->seq == seq) break;
+        CU_TRY(inst, cudaStreamSynchronize(inst->stream));
+        if (h->seq != seq)
+        {
+          inst->err = "reduction result was not published";
+          return PLK_ERR_CUDA;
+        }
+        break;
+      }
+      if (q != cudaErrorNotReady) CU_TRY(inst, q);
+    }
+  }
+  if (out0) *out0 = h->val[0];
+  if (out1) *out1 = h->val[1];
+  if (warn) *warn = h->warn;
+  return PLK_OK;
+}
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char *plk_version(void) { return "phyml_b200 0.1 (sm_100a)"; }
+
+const char *plk_last_error(const plk_instance *inst) { return inst ? inst->err.c_str() : g_create_error.c_str(); }
+
+int plk_create(const plk_config *cfg, plk_instance **out)
+{
+  if (!cfg || !out)
+  {
+    g_create_error = "null argument";
+    return PLK_ERR_ARG;
+  }
+  *out = nullptr;
+  if (cfg->n_tips < 1 || cfg->n_patterns < 1 || cfg->ns < 2 || cfg->ns > kMaxNs || cfg->ncatg < 1 ||
+      cfg->ncatg > kMaxCatg || cfg->n_clv < 1 || cfg->n_pmat < 1)
+  {
+    g_create_error = "plk_create: sizes out of range (2 <= ns <= 32, 1 <= ncatg <= 16)";
+    return PLK_ERR_ARG;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev < 1)
+  {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this engine has no CPU fallback)";
+    return PLK_ERR_CUDA;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev)
+  {
+    g_create_error = "plk_create: device ordinal out of range";
+    return PLK_ERR_ARG;
+  }
+  plk_instance *inst = new plk_instance();
+  inst->cfg = *cfg;
+  inst->apply_scaling = (cfg->flags & PLK_FLAG_NO_SCALING) ? 0 : 1;
+  auto fail = [&](int rc) {
+    g_create_error = inst->err;
+    plk_destroy(inst);
+    return rc;
+  };
+#define CREATE_TRY(call)                                             \
+  do                                                                 \
+  {                                                                  \
+    cudaError_t e_ = (call);                                         \
+    if (e_ != cudaSuccess)                                           \
+    {                                                                \
+      inst->err = std::string(#call) + ": " + cudaGetErrorString(e_); \
+      return fail(PLK_ERR_CUDA);                                     \
+    }                                                                \
+  } while (0)
+#define CREATE_RC(call)        \
+  do                           \
+  {                            \
+    int rc_ = (call);          \
+    if (rc_) return fail(rc_); \
+  } while (0)
+
+  CREATE_TRY(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CREATE_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+  inst->num_sms = prop.multiProcessorCount;
+  if (const char *e = getenv("PLK_TRAV_UMAX")) inst->trav_umax = (atoi(e) == 1) ? 1 : 2;
+  if (const char *e = getenv("PLK_TRAV_BLOCKS_PER_SM")) inst->trav_blocks_per_sm = std::max(1, std::min(4, atoi(e)));
+  CREATE_TRY(cudaStreamCreateWithFlags(&inst->stream, cudaStreamNonBlocking));
+
+  const size_t P = (size_t)cfg->n_patterns;
+  inst->tip_stride = (P + 127) & ~(size_t)127;
+  inst->pmat_elems = (size_t)cfg->ncatg * cfg->ns * cfg->ns;
+  inst->pmat_stride = inst->pmat_elems + (cfg->ns == 4 ? (size_t)cfg->ncatg * 64 : 0);
+  inst->clv.assign(cfg->n_clv, nullptr);
+  inst->scale.assign(cfg->n_clv, nullptr);
+
+  CREATE_RC(dev_alloc(inst, &inst->d_wght, P));
+  CREATE_RC(dev_alloc(inst, &inst->d_invar, P));
+  CREATE_RC(dev_alloc(inst, &inst->d_tipmask, 256));
+  CREATE_RC(dev_alloc(inst, &inst->d_tipcodes, inst->tip_stride * cfg->n_tips));
+  CREATE_RC(dev_alloc(inst, &inst->d_model, 1));
+  CREATE_RC(dev_alloc(inst, &inst->d_pmat, inst->pmat_stride * cfg->n_pmat));
+  CREATE_RC(dev_alloc(inst, &inst->d_site_lnl, P));
+  CREATE_RC(dev_alloc(inst, &inst->d_site_lk, P));
+  CREATE_RC(dev_alloc(inst, &inst->d_site_lk_cat, P * cfg->ncatg));
+  CREATE_RC(dev_alloc(inst, &inst->d_fact, P));
+  CREATE_RC(dev_alloc(inst, &inst->d_partials, (size_t)kMaxReduceBlocks * 2));
+  CREATE_RC(dev_alloc(inst, &inst->d_warn, 1));
+  CREATE_RC(dev_alloc(inst, &inst->d_result, 4));
+  CREATE_RC(dev_alloc(inst, &inst->d_stage, (size_t)kStageSlots * kStageBytes));
+  CREATE_TRY(cudaMemsetAsync(inst->d_wght, 0, P * sizeof(double), inst->stream));
+  CREATE_TRY(cudaMemsetAsync(inst->d_invar, 0xff, P * sizeof(short), inst->stream));
+  CREATE_TRY(cudaMemsetAsync(inst->d_tipmask, 0, 256 * sizeof(uint32_t), inst->stream));
+  CREATE_TRY(cudaMemsetAsync(inst->d_tipcodes, 0, inst->tip_stride * cfg->n_tips, inst->stream));
+  CREATE_TRY(cudaMemsetAsync(inst->d_warn, 0, sizeof(int), inst->stream));
+  CREATE_TRY(cudaMemsetAsync(inst->d_pmat, 0, inst->pmat_stride * cfg->n_pmat * sizeof(double), inst->stream));
+  CREATE_TRY(cudaMemsetAsync(inst->d_fact, 0, P * sizeof(int), inst->stream));
+
+  CREATE_TRY(cudaHostAlloc((void **)&inst->h_result, sizeof(ResultHost), cudaHostAllocMapped));
+  memset(inst->h_result, 0, sizeof(ResultHost));
+  CREATE_TRY(cudaHostGetDevicePointer((void **)&inst->h_result_dev, inst->h_result, 0));
+  for (int s = 0; s < kStageSlots; ++s)
+  {
+    CREATE_TRY(cudaHostAlloc((void **)&inst->h_stage[s], kStageBytes, cudaHostAllocDefault));
+    CREATE_TRY(cudaEventCreateWithFlags(&inst->stage_ev[s], cudaEventDisableTiming));
+  }
+  CREATE_TRY(cudaStreamSynchronize(inst->stream));
+#undef CREATE_TRY
+#undef CREATE_RC
+  *out = inst;
+  return PLK_OK;
+}
+
+void plk_destroy(plk_instance *inst)
+{
+  if (!inst) return;
+  cudaSetDevice(inst->cfg.device);
+  if (inst->stream) cudaStreamSynchronize(inst->stream);
+  if (inst->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(inst->comm);
+  for (double *p : inst->clv) cudaFree(p);
+  for (int *p : inst->scale) cudaFree(p);
+  cudaFree(inst->d_wght);
+  cudaFree(inst->d_invar);
+  cudaFree(inst->d_tipmask);
+  cudaFree(inst->d_tipcodes);
+  cudaFree(inst->d_model);
+  cudaFree(inst->d_pmat);
+  cudaFree(inst->d_site_lnl);
+  cudaFree(inst->d_site_lk);
+  cudaFree(inst->d_site_lk_cat);
+  cudaFree(inst->d_fact);
+  cudaFree(inst->d_dot_prod);
+  cudaFree(inst->d_partials);
+  cudaFree(inst->d_warn);
+  cudaFree(inst->d_result);
+  cudaFree(inst->d_stage);
+  if (inst->h_result) cudaFreeHost(inst->h_result);
+  for (int s = 0; s < kStageSlots; ++s)
+  {
+    if (inst->h_stage[s]) cudaFreeHost(inst->h_stage[s]);
+    if (inst->stage_ev[s]) cudaEventDestroy(inst->stage_ev[s]);
+  }
+  if (inst->stream) cudaStreamDestroy(inst->stream);
+  delete inst;
+}
+
+int plk_sync(plk_instance *inst)
+{
+  CU_TRY(inst, cudaStreamSynchronize(inst->stream));
+  return PLK_OK;
+}
+
+// ---- uploads -----------------------------------------------------------------------------------
+int plk_set_pattern_weights(plk_instance *inst, const double *wght, const short *invar)
+{
+  ARG_CHECK(inst, wght != nullptr, "wght is NULL");
+  const size_t P = inst->cfg.n_patterns;
+  CU_TRY(inst, cudaMemcpyAsync(inst->d_wght, wght, P * sizeof(double), cudaMemcpyHostToDevice, inst->stream));
+  if (invar)
+    CU_TRY(inst, cudaMemcpyAsync(inst->d_invar, invar, P * sizeof(short), cudaMemcpyHostToDevice, inst->stream));
+  return PLK_OK;
+}
+
+static int upload_masks(plk_instance *inst)
+{
+  uint32_t tmp[256];
+  memset(tmp, 0, sizeof(tmp));
+  for (size_t i = 0; i < inst->masks.size(); ++i) tmp[i] = inst->masks[i];
+  void *d = nullptr;
+  int   rc = stage_upload(inst, tmp, sizeof(tmp), &d);
+  if (rc) return rc;
+  CU_TRY(inst, cudaMemcpyAsync(inst->d_tipmask, d, sizeof(tmp), cudaMemcpyDeviceToDevice, inst->stream));
+  return PLK_OK;
+}
+
+int plk_set_tip_table(plk_instance *inst, int n_codes, const double *vectors)
+{
+  ARG_CHECK(inst, n_codes >= 1 && n_codes <= 256 && vectors, "tip table: 1..256 codes");
+  const int ns = inst->cfg.ns;
+  inst->tip_table.assign(vectors, vectors + (size_t)n_codes * ns);
+  inst->masks.assign(n_codes, 0u);
+  inst->mask_to_code.clear();
+  for (int c = 0; c < n_codes; ++c)
+  {
+    uint32_t m = 0;
+    for (int k = 0; k < ns; ++k)
+      if (vectors[(size_t)c * ns + k] > 0.0) m |= (1u << k);
+    inst->masks[c] = m;
+    if (!inst->mask_to_code.count(m)) inst->mask_to_code[m] = c;
+  }
+  return upload_masks(inst);
+}
+
+int plk_set_tip_codes(plk_instance *inst, int tip, const uint8_t *codes)
+{
+  ARG_CHECK(inst, tip >= 0 && tip < inst->cfg.n_tips && codes, "tip index out of range");
+  CU_TRY(inst, cudaMemcpyAsync(inst->d_tipcodes + (size_t)tip * inst->tip_stride, codes, inst->cfg.n_patterns,
+                               cudaMemcpyHostToDevice, inst->stream));
+  return PLK_OK;
+}
+
+int plk_set_all_tip_codes(plk_instance *inst, const uint8_t *codes, size_t host_stride)
+{
+  ARG_CHECK(inst, codes && host_stride >= (size_t)inst->cfg.n_patterns, "plk_set_all_tip_codes: bad arguments");
+  CU_TRY(inst, cudaMemcpy2DAsync(inst->d_tipcodes, inst->tip_stride, codes, host_stride, inst->cfg.n_patterns,
+                                 inst->cfg.n_tips, cudaMemcpyHostToDevice, inst->stream));
+  return PLK_OK;
+}
+
+int plk_set_tip_vectors(plk_instance *inst, int tip, const double *v)
+{
+  ARG_CHECK(inst, tip >= 0 && tip < inst->cfg.n_tips && v, "tip index out of range");
+  const int            ns = inst->cfg.ns, P = inst->cfg.n_patterns;
+  std::vector<uint8_t> codes(P);
+  bool                 table_grew = false;
+  for (int s = 0; s < P; ++s)
+  {
+    uint32_t m = 0;
+    for (int k = 0; k < ns; ++k)
+      if (v[(size_t)s * ns + k] > 0.0) m |= (1u << k);
+    auto it = inst->mask_to_code.find(m);
+    int  code;
+    if (it == inst->mask_to_code.end())
+    {
+      ARG_CHECK(inst, inst->masks.size() < 256, "more than 256 distinct tip state sets");
+      code = (int)inst->masks.size();
+      inst->masks.push_back(m);
+      inst->mask_to_code[m] = code;
+      for (int k = 0; k < ns; ++k) inst->tip_table.push_back((m >> k) & 1u ? 1.0 : 0.0);
+      table_grew = true;
+    }
+    else
+      code = it->second;
+    codes[s] = (uint8_t)code;
+  }
+  if (table_grew)
+  {
+    int rc = upload_masks(inst);
+    if (rc) return rc;
+  }
+  int rc = plk_set_tip_codes(inst, tip, codes.data());
+  if (rc) return rc;
+  CU_TRY(inst, cudaStreamSynchronize(inst->stream));  // `codes` is a local buffer
+  return PLK_OK;
+}
+
+int plk_set_model(plk_instance *inst, const double *U, const double *V, const double *lambda, const double *pi,
+                  const double *rates, const double *rate_probs, double pinv, int invar_flag, double l_min,
+                  double l_max, double br_len_mult)
+{
+  ARG_CHECK(inst, U && V && lambda && pi && rates && rate_probs, "plk_set_model: NULL array");
+  const int ns = inst->cfg.ns, nc = inst->cfg.ncatg;
+  ModelDev *m = new ModelDev();
+  memset(m, 0, sizeof(ModelDev));
+  memcpy(m->U, U, sizeof(double) * ns * ns);
+  memcpy(m->V, V, sizeof(double) * ns * ns);
+  memcpy(m->lambda, lambda, sizeof(double) * ns);
+  memcpy(m->pi, pi, sizeof(double) * ns);
+  memcpy(m->rates, rates, sizeof(double) * nc);
+  memcpy(m->probs, rate_probs, sizeof(double) * nc);
+  m->pinv = pinv;
+  m->invar_flag = invar_flag;
+  m->l_min = l_min;
+  m->l_max = l_max;
+  m->br_len_mult = br_len_mult;
+  void *d = nullptr;
+  int   rc = stage_upload(inst, m, sizeof(ModelDev), &d);
+  delete m;
+  if (rc) return rc;
+  CU_TRY(inst, cudaMemcpyAsync(inst->d_model, d, sizeof(ModelDev), cudaMemcpyDeviceToDevice, inst->stream));
+  inst->eigen_ready = false;
+  inst->l_min = l_min;
+  inst->l_max = l_max;
+  return PLK_OK;
+}
+
+// ---- K0 ------------------------------------------------------------------------------------------
+int plk_update_pmats(plk_instance *inst, int n, const int *pmat, const double *l)
+{
+  ARG_CHECK(inst, n >= 0 && (n == 0 || (pmat && l)), "plk_update_pmats: bad arguments");
+  const int    ns = inst->cfg.ns, nc = inst->cfg.ncatg;
+  const int    per_slot = (int)(kStageBytes / sizeof(PmatJob));
+  const int    threads = ((ns * ns + 31) / 32) * 32;
+  const size_t smem = (size_t)(kMaxNs + ns * ns) * sizeof(double);
+  for (int off = 0; off < n; off += per_slot)
+  {
+    const int             cnt = std::min(per_slot, n - off);
+    std::vector<PmatJob> jobs(cnt);
+    for (int i = 0; i < cnt; ++i)
+    {
+      const int h = pmat[off + i];
+      ARG_CHECK(inst, h >= 0 && h < inst->cfg.n_pmat, "pmat handle out of range");
+      jobs[i].P = inst->d_pmat + (size_t)h * inst->pmat_stride;
+      jobs[i].l = l[off + i];
+    }
+    void *d = nullptr;
+    int   rc = stage_upload(inst, jobs.data(), sizeof(PmatJob) * cnt, &d);
+    if (rc) return rc;
+    k_pmat<<<cnt * nc, threads, smem, inst->stream>>>((const PmatJob *)d, inst->d_model, ns, nc, ns == 4 ? 1 : 0);
+    inst->launches++;
+    CU_TRY(inst, cudaGetLastError());
+  }
+  return PLK_OK;
+}
+
+int plk_set_pmat(plk_instance *inst, int pmat, const double *P)
+{
+  ARG_CHECK(inst, pmat >= 0 && pmat < inst->cfg.n_pmat && P, "pmat handle out of range");
+  std::vector<double> rec(inst->pmat_stride);
+  memcpy(rec.data(), P, inst->pmat_elems * sizeof(double));
+  if (inst->cfg.ns == 4)
+  {  // tip table TP[c][mask][i] = sum_{j in mask} P[c][i][j], ascending j (same order as k_pmat)
+    for (int c = 0; c < inst->cfg.ncatg; ++c)
+      for (int m = 0; m < 16; ++m)
+        for (int i = 0; i < 4; ++i)
+        {
+          const double *row = P + (size_t)c * 16 + i * 4;
+          double        a = (m & 1) ? row[0] : 0.0;
+          if (m & 2) a = a + row[1];
+          if (m & 4) a = a + row[2];
+          if (m & 8) a = a + row[3];
+          rec[inst->pmat_elems + (size_t)c * 64 + tip_row4(m) * 4 + i] = a;
+        }
+  }
+  const size_t b = inst->pmat_stride * sizeof(double);
+  double      *dstp = inst->d_pmat + (size_t)pmat * inst->pmat_stride;
+  if (b <= kStageBytes)
+  {
+    void *d = nullptr;
+    int   rc = stage_upload(inst, rec.data(), b, &d);
+    if (rc) return rc;
+    CU_TRY(inst, cudaMemcpyAsync(dstp, d, b, cudaMemcpyDeviceToDevice, inst->stream));
+  }
+  else
+  {
+    CU_TRY(inst, cudaMemcpyAsync(dstp, rec.data(), b, cudaMemcpyHostToDevice, inst->stream));
+    CU_TRY(inst, cudaStreamSynchronize(inst->stream));
+  }
+  return PLK_OK;
+}
+
+int plk_get_pmat(plk_instance *inst, int pmat, double *P)
+{
+  ARG_CHECK(inst, pmat >= 0 && pmat < inst->cfg.n_pmat && P, "pmat handle out of range");
+  CU_TRY(inst, cudaMemcpyAsync(P, inst->d_pmat + (size_t)pmat * inst->pmat_stride, inst->pmat_elems * sizeof(double),
+                               cudaMemcpyDeviceToHost, inst->stream));
+  CU_TRY(inst, cudaStreamSynchronize(inst->stream));
+  return PLK_OK;
+}
+
+// ---- K1 ------------------------------------------------------------------------------------------
+}  // extern "C"
+
+// per-level launch of the generic kernel (ns != 4 or ncatg not a power of two)
+static int launch_level_generic(plk_instance *inst, const OpDev *d_ops, int n_ops)
+{
+  const int ns = inst->cfg.ns, nc = inst->cfg.ncatg, P = inst->cfg.n_patterns;
+  int       bpo = std::max(1, (P + 127) / 128);
+  k_partial_generic<<<(unsigned)(bpo * n_ops), 128, 0, inst->stream>>>(d_ops, bpo, P, ns, nc, inst->d_wght,
+                                                                        inst->d_tipmask, inst->apply_scaling);
+  inst->launches++;
+  CU_TRY(inst, cudaGetLastError());
+  return PLK_OK;
+}
+
+template <int NCATG, int UMAX>
+static int launch_traverse_t(plk_instance *inst, const OpDev *d_ops, int n_ops, int tile_sites, int n_tiles, int grid)
+{
+  k_traverse_dna<NCATG, UMAX><<<grid, kTravThreads, 0, inst->stream>>>(d_ops, n_ops, inst->cfg.n_patterns, tile_sites,
+                                                                       n_tiles, inst->d_wght, inst->d_tipmask,
+                                                                       inst->apply_scaling);
+  inst->launches++;
+  CU_TRY(inst, cudaGetLastError());
+  return PLK_OK;
+}
+
+// fused traversal launch: tiles of `tile_sites` patterns, persistent blocks (2 per SM), every block
+// gets the same number of equally sized tiles so there is no tail wave
+static int launch_traverse(plk_instance *inst, const OpDev *d_ops, int n_ops)
+{
+  const int nc = inst->cfg.ncatg, P = inst->cfg.n_patterns;
+  const int CT = kTravComputeWarps * 32;
+  const int umax = inst->trav_umax;
+  const int slots = inst->num_sms * inst->trav_blocks_per_sm;
+  const long long items = (long long)P * nc;
+  const long long cap = (long long)slots * CT * umax;  // items resident in one round
+  const int       rounds = (int)((items + cap - 1) / cap);
+  int             n_tiles = slots * rounds;
+  // do not cut tiles below one pass of the block
+  const int min_tile = std::max(1, CT / nc);
+  n_tiles = std::max(1, std::min(n_tiles, (P + min_tile - 1) / min_tile));
+  int tile_sites = (P + n_tiles - 1) / n_tiles;
+  n_tiles = (P + tile_sites - 1) / tile_sites;
+  const int grid = std::min(n_tiles, slots);
+  if ((long long)tile_sites * nc > (long long)CT * umax)
+  {
+    inst->err = "internal: traversal tile exceeds block capacity";
+    return PLK_ERR_ARG;
+  }
+#define TRAV_CASE(NC)                                                                          \
+  case NC:                                                                                     \
+    return umax == 2 ? launch_traverse_t<NC, 2>(inst, d_ops, n_ops, tile_sites, n_tiles, grid) \
+                     : launch_traverse_t<NC, 1>(inst, d_ops, n_ops, tile_sites, n_tiles, grid);
+  switch (nc)
+  {
+    TRAV_CASE(1)
+    TRAV_CASE(2)
+    TRAV_CASE(4)
+    TRAV_CASE(8)
+  }
+#undef TRAV_CASE
+  inst->err = "internal: unsupported ncatg for traversal kernel";
+  return PLK_ERR_ARG;
+}
+
+extern "C" {
+
+int plk_update_partials(plk_instance *inst, int n_ops, const plk_op *ops)
+{
+  ARG_CHECK(inst, n_ops >= 0 && (n_ops == 0 || ops), "plk_update_partials: bad arguments");
+  if (n_ops == 0) return PLK_OK;
+  const int  nclv = inst->cfg.n_clv;
+  const int  nc = inst->cfg.ncatg;
+  const bool fused = (inst->cfg.ns == 4) && (nc == 1 || nc == 2 || nc == 4 || nc == 8);
+  // dependency levels: an op runs after the last writer of each operand it reads, after the last
+  // reader of the buffer it overwrites and after the last writer of that buffer (RAW, WAR, WAW)
+  inst->lvl_write.assign(nclv, -1);
+  inst->lvl_read.assign(nclv, -1);
+  inst->op_level.assign(n_ops, 0);
+  int max_level = 0;
+  for (int i = 0; i < n_ops; ++i)
+  {
+    const plk_op &o = ops[i];
+    ARG_CHECK(inst, o.dst >= 0 && o.dst < nclv, "dst handle out of range");
+    ARG_CHECK(inst, o.pmat1 >= 0 && o.pmat1 < inst->cfg.n_pmat && o.pmat2 >= 0 && o.pmat2 < inst->cfg.n_pmat,
+              "pmat handle out of range");
+    int rc = check_side(inst, o.c1, false);
+    if (rc) return rc;
+    rc = check_side(inst, o.c2, false);
+    if (rc) return rc;
+    int lv = std::max(inst->lvl_write[o.dst], inst->lvl_read[o.dst]) + 1;
+    const plk_side *cs[2] = {&o.c1, &o.c2};
+    for (const plk_side *c : cs)
+      if (c->clv >= 0)
+      {
+        ARG_CHECK(inst, c->clv != o.dst, "an update cannot read the buffer it writes");
+        if (inst->lvl_write[c->clv] < 0)
+          ARG_CHECK(inst, inst->clv[c->clv] != nullptr, "operand CLV was never computed");
+        lv = std::max(lv, inst->lvl_write[c->clv] + 1);
+      }
+    if (lv < 0) lv = 0;
+    inst->op_level[i] = lv;
+    inst->lvl_write[o.dst] = lv;
+    for (const plk_side *c : cs)
+      if (c->clv >= 0) inst->lvl_read[c->clv] = std::max(inst->lvl_read[c->clv], lv);
+    max_level = std::max(max_level, lv);
+    rc = ensure_clv(inst, o.dst);
+    if (rc) return rc;
+  }
+  std::vector<int> order(n_ops);
+  if (fused)
+  {
+    // the fused kernel executes the list in program order per thread: the caller's order is valid
+    for (int i = 0; i < n_ops; ++i) order[i] = i;
+  }
+  else
+  {  // stable bucket by level
+    std::vector<int> cnt(max_level + 2, 0);
+    for (int i = 0; i < n_ops; ++i) cnt[inst->op_level[i] + 1]++;
+    for (int l = 0; l <= max_level; ++l) cnt[l + 1] += cnt[l];
+    for (int i = 0; i < n_ops; ++i) order[cnt[inst->op_level[i]]++] = i;
+  }
+  const int per_slot = (int)(kStageBytes / sizeof(OpDev));
+  std::vector<OpDev> host;
+  host.reserve(std::min(n_ops, per_slot));
+  int pos = 0;
+  while (pos < n_ops)
+  {
+    host.clear();
+    std::vector<std::pair<int, int>> launches;  // (offset in block, count): one per level chunk / fused chunk
+    while (pos < n_ops && (int)host.size() < per_slot)
+    {
+      const int lv = inst->op_level[order[pos]];
+      const int start = (int)host.size();
+      while (pos < n_ops && (fused || inst->op_level[order[pos]] == lv) && (int)host.size() < per_slot)
+      {
+        const plk_op &o = ops[order[pos]];
+        OpDev         d;
+        d.dst = inst->clv[o.dst];
+        d.dst_scale = inst->scale[o.dst];
+        plk_side x = o.c1, y = o.c2;
+        int      px = o.pmat1, py = o.pmat2;
+        int      kind = 0;
+        if (fused)
+        {
+          // canonical operand order (the product of the children commutes exactly): a child that is
+          // the previous update's destination first (forwarded in registers), CLVs before tips
+          const double *prev_dst = ((int)host.size() > start) ? host.back().dst : nullptr;
+          const bool    yfwd = y.clv >= 0 && prev_dst && inst->clv[y.clv] == prev_dst;
+          const bool    xfwd = x.clv >= 0 && prev_dst && inst->clv[x.clv] == prev_dst;
+          if ((yfwd && !xfwd) || (!xfwd && x.tip >= 0 && y.clv >= 0))
+          {
+            std::swap(x, y);
+            std::swap(px, py);
+          }
+          const bool afwd = x.clv >= 0 && prev_dst && inst->clv[x.clv] == prev_dst;
+          const int  ka = afwd ? kSrcFwd : (x.clv >= 0 ? kSrcSlot : kSrcTip);
+          const int  kb = (y.tip >= 0) ? kSrcTip : (ka == kSrcSlot ? kSrcLate : kSrcSlot);
+          kind = ka | (kb << 2);
+        }
+        const SideDev a = side_dev(inst, x), b = side_dev(inst, y);
+        d.c1 = a.clv;
+        d.s1 = a.scale;
+        d.t1 = a.tip;
+        d.c2 = b.clv;
+        d.s2 = b.scale;
+        d.t2 = b.tip;
+        d.P1 = inst->d_pmat + (size_t)px * inst->pmat_stride;
+        d.P2 = inst->d_pmat + (size_t)py * inst->pmat_stride;
+        if (fused)
+        {  // tip operands read the edge's tip table instead of P
+          if (x.tip >= 0) d.P1 += inst->pmat_elems;
+          if (y.tip >= 0) d.P2 += inst->pmat_elems;
+        }
+        d.flags = kind;
+        d.pad[0] = d.pad[1] = d.pad[2] = 0;
+        host.push_back(d);
+        ++pos;
+      }
+      launches.emplace_back(start, (int)host.size() - start);
+    }
+    void *d = nullptr;
+    int   rc = stage_upload(inst, host.data(), host.size() * sizeof(OpDev), &d);
+    if (rc) return rc;
+    for (auto &lc : launches)
+    {
+      rc = fused ? launch_traverse(inst, (const OpDev *)d + lc.first, lc.second)
+                 : launch_level_generic(inst, (const OpDev *)d + lc.first, lc.second);
+      if (rc) return rc;
+    }
+  }
+  return PLK_OK;
+}
+
+// ---- K2 ------------------------------------------------------------------------------------------
+int plk_edge_lnl(plk_instance *inst, plk_side left, plk_side rght, int pmat, double *lnl, int *warn)
+{
+  int rc = check_side(inst, left, true);
+  if (rc) return rc;
+  rc = check_side(inst, rght, true);
+  if (rc) return rc;
+  ARG_CHECK(inst, pmat >= 0 && pmat < inst->cfg.n_pmat && lnl, "plk_edge_lnl: bad arguments");
+  const int grid = reduce_grid(inst, 128);
+  k_edge_lnl<<<grid, 128, 0, inst->stream>>>(side_dev(inst, left), side_dev(inst, rght),
+                                             inst->d_pmat + (size_t)pmat * inst->pmat_stride, inst->d_model,
+                                             inst->cfg.n_patterns, inst->cfg.ns, inst->cfg.ncatg, inst->d_wght,
+                                             inst->d_invar, inst->d_tipmask, inst->d_site_lnl, inst->d_site_lk,
+                                             inst->d_site_lk_cat, inst->d_fact, inst->d_partials, inst->d_warn);
+  inst->launches++;
+  CU_TRY(inst, cudaGetLastError());
+  inst->site_valid = true;
+  return finish_reduction(inst, grid, 1, lnl, nullptr, warn);
+}
+
+// ---- K3 ------------------------------------------------------------------------------------------
+int plk_eigen_lr(plk_instance *inst, plk_side left, plk_side rght)
+{
+  int rc = check_side(inst, left, true);
+  if (rc) return rc;
+  rc = check_side(inst, rght, true);
+  if (rc) return rc;
+  if (!inst->d_dot_prod)
+  {
+    rc = dev_alloc(inst, &inst->d_dot_prod, clv_elems(inst));
+    if (rc) return rc;
+    CU_TRY(inst, cudaMemsetAsync(inst->d_dot_prod, 0, clv_elems(inst) * sizeof(double), inst->stream));
+  }
+  const long long work = (long long)inst->cfg.n_patterns * inst->cfg.ncatg;
+  const int       grid = (int)std::max<long long>(1, std::min<long long>((work + 127) / 128, inst->num_sms * 32));
+  k_eigen_lr<<<grid, 128, 0, inst->stream>>>(side_dev(inst, left), side_dev(inst, rght), inst->d_model,
+                                             inst->cfg.n_patterns, inst->cfg.ns, inst->cfg.ncatg, inst->d_wght,
+                                             inst->d_tipmask, inst->d_dot_prod, inst->d_fact);
+  inst->launches++;
+  CU_TRY(inst, cudaGetLastError());
+  inst->eigen_ready = true;
+  return PLK_OK;
+}
+
+// ---- K4 ------------------------------------------------------------------------------------------
+static int run_k4(plk_instance *inst, double l, int deriv, double *lnl, double *dlnl, int *warn)
+{
+  if (!inst->eigen_ready)
+  {
+    inst->err = "plk_edge_lnl_dlnl / _eigen called before plk_eigen_lr (update_eigen_lr)";
+    return PLK_ERR_STATE;
+  }
+  const int grid = reduce_grid(inst, 128);
+  k_lnl_dlnl<<<grid, 128, 0, inst->stream>>>(inst->d_dot_prod, inst->d_fact, inst->d_model, l, deriv,
+                                             inst->cfg.n_patterns, inst->cfg.ns, inst->cfg.ncatg, inst->d_wght,
+                                             inst->d_invar, inst->d_site_lnl, inst->d_partials, inst->d_warn);
+  inst->launches++;
+  CU_TRY(inst, cudaGetLastError());
+  return finish_reduction(inst, grid, 2, lnl, dlnl, warn);
+}
+
+int plk_edge_lnl_dlnl(plk_instance *inst, double *l, double *lnl, double *dlnl, int *warn)
+{
+  ARG_CHECK(inst, l && lnl && dlnl, "plk_edge_lnl_dlnl: NULL argument");
+  ARG_CHECK(inst, *l == *l, "plk_edge_lnl_dlnl: length is NaN");  // lk.c:671
+  // lk.c:673-674
+  if (*l < inst->l_min)
+    *l = inst->l_min;
+  else if (*l > inst->l_max)
+    *l = inst->l_max;
+  return run_k4(inst, *l, 1, lnl, dlnl, warn);
+}
+
+int plk_edge_lnl_eigen(plk_instance *inst, double l, double *lnl, int *warn)
+{
+  ARG_CHECK(inst, lnl, "plk_edge_lnl_eigen: NULL argument");
+  double dummy;
+  return run_k4(inst, l, 0, lnl, &dummy, warn);
+}
+
+// ---- read-backs ------------------------------------------------------------------------------------
+int plk_get_clv(plk_instance *inst, int h, double *clv_out, int *scale_out)
+{
+  ARG_CHECK(inst, h >= 0 && h < inst->cfg.n_clv, "clv handle out of range");
+  ARG_CHECK(inst, inst->clv[h] != nullptr, "clv handle was never written");
+  if (clv_out)
+    CU_TRY(inst, cudaMemcpyAsync(clv_out, inst->clv[h], clv_elems(inst) * sizeof(double), cudaMemcpyDeviceToHost,
+                                 inst->stream));
+  if (scale_out)
+    CU_TRY(inst, cudaMemcpyAsync(scale_out, inst->scale[h], (size_t)inst->cfg.n_patterns * sizeof(int),
+                                 cudaMemcpyDeviceToHost, inst->stream));
+  CU_TRY(inst, cudaStreamSynchronize(inst->stream));
+  return PLK_OK;
+}
+
+int plk_set_clv(plk_instance *inst, int h, const double *clv_in, const int *scale_in)
+{
+  ARG_CHECK(inst, h >= 0 && h < inst->cfg.n_clv && clv_in, "clv handle out of range");
+  int rc = ensure_clv(inst, h);
+  if (rc) return rc;
+  CU_TRY(inst, cudaMemcpyAsync(inst->clv[h], clv_in, clv_elems(inst) * sizeof(double), cudaMemcpyHostToDevice,
+                               inst->stream));
+  if (scale_in)
+    CU_TRY(inst, cudaMemcpyAsync(inst->scale[h], scale_in, (size_t)inst->cfg.n_patterns * sizeof(int),
+                                 cudaMemcpyHostToDevice, inst->stream));
+  CU_TRY(inst, cudaStreamSynchronize(inst->stream));
+  return PLK_OK;
+}
+
+int plk_get_site_lnl(plk_instance *inst, double *site_lnl, double *site_lk, double *site_lk_cat, int *fact)
+{
+  const size_t P = inst->cfg.n_patterns;
+  if (site_lnl)
+    CU_TRY(inst, cudaMemcpyAsync(site_lnl, inst->d_site_lnl, P * sizeof(double), cudaMemcpyDeviceToHost, inst->stream));
+  if (site_lk)
+    CU_TRY(inst, cudaMemcpyAsync(site_lk, inst->d_site_lk, P * sizeof(double), cudaMemcpyDeviceToHost, inst->stream));
+  if (site_lk_cat)
+    CU_TRY(inst, cudaMemcpyAsync(site_lk_cat, inst->d_site_lk_cat, P * inst->cfg.ncatg * sizeof(double),
+                                 cudaMemcpyDeviceToHost, inst->stream));
+  if (fact) CU_TRY(inst, cudaMemcpyAsync(fact, inst->d_fact, P * sizeof(int), cudaMemcpyDeviceToHost, inst->stream));
+  CU_TRY(inst, cudaStreamSynchronize(inst->stream));
+  return PLK_OK;
+}
+
+int plk_get_dot_prod(plk_instance *inst, double *dot_prod)
+{
+  ARG_CHECK(inst, dot_prod && inst->d_dot_prod, "dot_prod not computed yet");
+  CU_TRY(inst, cudaMemcpyAsync(dot_prod, inst->d_dot_prod, clv_elems(inst) * sizeof(double), cudaMemcpyDeviceToHost,
+                               inst->stream));
+  CU_TRY(inst, cudaStreamSynchronize(inst->stream));
+  return PLK_OK;
+}
+
+// ---- NCCL ------------------------------------------------------------------------------------------
+int plk_comm_unique_id(void *id128)
+{
+  if (!id128) return PLK_ERR_ARG;
+  if (!g_nccl.load(g_create_error)) return PLK_ERR_NCCL;
+  NcclApi::UniqueId id;
+  const int         rc = g_nccl.GetUniqueId(&id);
+  if (rc != 0)
+  {
+    g_create_error = "ncclGetUniqueId failed";
+    return PLK_ERR_NCCL;
+  }
+  memcpy(id128, &id, 128);
+  return PLK_OK;
+}
+
+int plk_comm_init(plk_instance *inst, int rank, int world, const void *id128)
+{
+  ARG_CHECK(inst, id128 && world >= 1 && rank >= 0 && rank < world, "plk_comm_init: bad arguments");
+  if (!g_nccl.load(inst->err)) return PLK_ERR_NCCL;
+  CU_TRY(inst, cudaSetDevice(inst->cfg.device));
+  NcclApi::UniqueId id;
+  memcpy(&id, id128, 128);
+  const int rc = g_nccl.CommInitRank(&inst->comm, world, id, rank);
+  if (rc != 0)
+  {
+    inst->err = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+    inst->comm = nullptr;
+    return PLK_ERR_NCCL;
+  }
+  inst->rank = rank;
+  inst->world = world;
+  inst->allreduce = true;
+  return PLK_OK;
+}
+
+int plk_comm_set_allreduce(plk_instance *inst, int enable)
+{
+  if (enable && !inst->comm)
+  {
+    inst->err = "plk_comm_set_allreduce: no communicator";
+    return PLK_ERR_STATE;
+  }
+  inst->allreduce = enable != 0;
+  return PLK_OK;
+}
+
+// ---- introspection -----------------------------------------------------------------------------------
+long long plk_launch_count(const plk_instance *inst) { return inst->launches; }
+size_t    plk_device_bytes(const plk_instance *inst) { return inst->bytes; }
+void     *plk_stream(plk_instance *inst) { return (void *)inst->stream; }
+
+}  // extern "C"

@@ -1,0 +1,1044 @@
+// phyml_b200/csrc/plk_kernels.cuh -- sm_100a kernels of the likelihood engine.
+//
+// K0  k_pmat            batched P(t) = U diag(exp(lambda t r_c)) V        (models.c:257-326, lk.c:2238-2325)
+// K1  k_traverse_dna    fused CLV updates for a whole op list, 4 states: 256-bit LDG/STG, op descriptors and
+//                       P-matrices streamed by a producer warp through a TMA/mbarrier ring (avx.c:301-522)
+//     k_partial_generic any ns <= 32 / any ncatg                          (lk.c:1659-1768)
+// K2  k_edge_lnl        edge log-likelihood + per-site by-products        (lk.c:605-645, 767-861, 2777-2801)
+// K3  k_eigen_lr        eigen-basis projection dot_prod                   (lk.c:1038-1114, avx.c:21-105)
+// K4  k_lnl_dlnl        lnL and dlnL/dl from dot_prod                     (lk.c:655-753, 955-1032)
+//     k_reduce_final    deterministic second stage of the lnL reductions
+//
+// Arithmetic order: where it is free, sums are accumulated in the order of the reference's AVX+FMA
+// kernels (first term a plain product, then an FMA chain in ascending state order; horizontal sums
+// as (x0+x2)+(x1+x3)), so CLVs and scalers come out bit-identical to the reference's AVX build for
+// identical inputs.  The file is compiled with -fmad=false: every fma() below is explicit.
+#pragma once
+#include <cfloat>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace plk
+{
+
+constexpr int kMaxNs = 32;
+constexpr int kMaxCatg = 16;
+constexpr double kLog2 = 0.69314718055994528623;  // utilities.h:267
+constexpr double kSmallPij = 1.E-100;              // utilities.h:478
+constexpr int kLarge = 256;                        // utilities.h:507
+
+// 2^256 and 2^-256 exactly (utilities.h:508-520)
+__device__ __forceinline__ double two_to_large() { return __longlong_as_double(0x4FF0000000000000LL); }
+__device__ __forceinline__ double inv_two_to_large() { return __longlong_as_double(0x2FF0000000000000LL); }
+
+struct __align__(32) double4a
+{
+  double x, y, z, w;
+};
+
+// Model block in device memory (uploaded by plk_set_model)
+struct ModelDev
+{
+  double U[kMaxNs * kMaxNs];
+  double V[kMaxNs * kMaxNs];
+  double lambda[kMaxNs];
+  double pi[kMaxNs];
+  double rates[kMaxCatg];
+  double probs[kMaxCatg];
+  double pinv, l_min, l_max, br_len_mult;
+  int    invar_flag;
+  int    pad;
+};
+
+// One CLV update with every handle resolved to device pointers.
+struct OpDev
+{
+  double        *dst;
+  int           *dst_scale;
+  const double  *c1;  // internal child CLV or nullptr
+  const int     *s1;
+  const uint8_t *t1;  // tip codes or nullptr
+  const double  *c2;
+  const int     *s2;
+  const uint8_t *t2;
+  const double  *P1;
+  const double  *P2;
+  int            flags;  // fused kernel: operand sources, kSrc* of child 1 | kSrc* of child 2 << 2
+  int            pad[3];
+};
+static_assert(sizeof(OpDev) == 96, "OpDev must be a multiple of 16 bytes for cp.async.bulk");
+// Operand sources of the fused traversal kernel.  The host canonicalises every update (the product
+// of the two children commutes exactly) to one of (FWD,TIP) (FWD,SLOT) (SLOT,TIP) (SLOT,LATE) (TIP,TIP):
+//   TIP  tip: P1/P2 points at the edge's tip table TP[cat][mask][state] written by k_pmat
+//   FWD  the destination of the previous update of the list, still in registers
+//   SLOT a CLV in global memory, prefetched one update ahead
+//   LATE a second CLV in global memory, loaded inside the update
+constexpr int kSrcTip = 0, kSrcFwd = 1, kSrcSlot = 2, kSrcLate = 3;
+
+// 4-state tip tables are stored by ROW = kTipRow[mask]: the unambiguous masks 1,2,4,8 get rows 0..3 so
+// that the 32-byte rows read by the lanes of a quarter-warp fall into different shared-memory banks.
+__host__ __device__ __forceinline__ int tip_row4(int mask)
+{
+  // rows:      mask 0->15, 1->0, 2->1, 3->4, 4->2, 5->5, 6->6, 7->7, 8->3, 9..14 -> 8..13, 15->14
+  return (int)((0xEDCBA9837652410FULL >> (4 * (mask & 15))) & 15ULL);
+}
+constexpr int kTipRowAllOnes = 14;
+
+// One side of an edge (K2/K3)
+struct SideDev
+{
+  const double  *clv;
+  const int     *scale;
+  const uint8_t *tip;
+};
+
+// ------------------------------------------------------------------------------------------------
+// mbarrier + TMA bulk-copy helpers (cp.async.bulk -> SASS UBLKCP): stage the P-matrices of an op
+// in shared memory.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0: one block per (P-matrix, rate category); one thread per matrix entry.
+struct PmatJob
+{
+  double *P;  // [ncatg][ns][ns]
+  double  l;  // b->l->v
+};
+
+__global__ void k_pmat(const PmatJob *__restrict__ jobs, const ModelDev *__restrict__ mod, int ns, int ncatg,
+                       int with_tip_table)
+{
+  extern __shared__ double sm[];  // expt[ns] | raw / normalised P of this category: [ns*ns]
+  double *expt = sm;
+  double *raw = sm + kMaxNs;
+  const int job = blockIdx.x / ncatg;
+  const int c = blockIdx.x % ncatg;
+  const int e = threadIdx.x;
+  const int nn = ns * ns;
+
+  // lk.c:2296-2300
+  double len = fmax(0.0, jobs[job].l) * mod->rates[c];
+  len = len * mod->br_len_mult;
+  if (len < mod->l_min)
+    len = mod->l_min;
+  else if (len > mod->l_max)
+    len = mod->l_max;
+
+  if (e < ns) expt[e] = exp(mod->lambda[e] * len);  // models.c:275
+  __syncthreads();
+  double acc = 0.0;
+  if (e < nn)
+  {
+    const int i = e / ns, j = e % ns;
+    for (int k = 0; k < ns; ++k) acc = fma(mod->U[i * ns + k] * expt[k], mod->V[k * ns + j], acc);  // models.c:279,291
+    if (acc < kSmallPij) acc = kSmallPij;                                                           // models.c:293
+    raw[e] = acc;
+  }
+  __syncthreads();
+  double pn = 0.0;
+  if (e < nn)
+  {
+    const int i = e / ns;
+    double    sum = 0.0;
+    for (int j = 0; j < ns; ++j) sum = sum + raw[i * ns + j];  // models.c:296-297
+    pn = raw[e] / sum;                                          // models.c:298
+    jobs[job].P[(size_t)c * nn + e] = pn;
+  }
+  if (with_tip_table)
+  {  // ns == 4: TP[c][tip_row4(mask)][i] = sum_{j in mask} P[c][i][j], ascending j (a tip child's vector)
+    __syncthreads();
+    if (e < nn) raw[e] = pn;
+    __syncthreads();
+    double *TP = jobs[job].P + (size_t)ncatg * nn + (size_t)c * 64;
+    for (int t = e; t < 64; t += blockDim.x)
+    {
+      const int m = t >> 2, i = t & 3;
+      double    a = (m & 1) ? raw[i * 4 + 0] : 0.0;
+      if (m & 2) a = a + raw[i * 4 + 1];
+      if (m & 4) a = a + raw[i * 4 + 2];
+      if (m & 8) a = a + raw[i * 4 + 3];
+      TP[tip_row4(m) * 4 + i] = a;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1, 4 states.  Thread <-> (site, category): its 4 states are one 32-byte vector, so consecutive
+// threads stream consecutive 32-byte words of each CLV (256-bit LDG/STG, fully coalesced).
+// The per-site max over all ncatg*4 entries is a shuffle over the NCATG neighbouring lanes.
+__device__ __forceinline__ double4a ld256(const double *p) { return *reinterpret_cast<const double4a *>(p); }
+__device__ __forceinline__ void     st256(double *p, const double4a &v) { *reinterpret_cast<double4a *>(p) = v; }
+
+// u = P . v in the order of AVX_Matrix_Vect_Prod (avx.c:593-616): first column a product, then FMAs
+__device__ __forceinline__ void matvec4(const double (&p)[16], const double4a &v, double (&u)[4])
+{
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+  {
+    double a = p[i * 4 + 0] * v.x;
+    a = fma(p[i * 4 + 1], v.y, a);
+    a = fma(p[i * 4 + 2], v.z, a);
+    a = fma(p[i * 4 + 3], v.w, a);
+    u[i] = a;
+  }
+}
+
+// tip child: v is a 0/1 vector given as a bit mask; same order, products with 0/1 are exact
+__device__ __forceinline__ void tipvec4(const double (&p)[16], uint32_t m, double (&u)[4])
+{
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+  {
+    double a = (m & 1u) ? p[i * 4 + 0] : 0.0;
+    if (m & 2u) a = a + p[i * 4 + 1];
+    if (m & 4u) a = a + p[i * 4 + 2];
+    if (m & 8u) a = a + p[i * 4 + 3];
+    u[i] = a;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 fused traversal, 4 states: ONE launch executes a whole dependency-ordered list of updates
+// (a post-order / pre-order traversal, or a single Update_Partial_Lk).  Site patterns are
+// independent, so each thread keeps the same (site, category) items for every update of the list:
+// an update only ever reads CLV words that the same thread wrote earlier in the list, i.e. no
+// grid-wide synchronisation is needed between tree levels, and freshly written children are
+// re-read from L2 instead of HBM.  Scalers are written by the category-0 lane of a site and read by
+// its sibling lanes: __syncwarp() after every update orders that.
+//
+// Warp roles: 8 compute warps + 1 producer warp.  The producer streams, S updates ahead, the
+// 80-byte update descriptor and the two ncatg x 4 x 4 P-matrices of each update into a
+// shared-memory ring with TMA bulk copies (cp.async.bulk -> UBLKCP) signalled on full[]
+// mbarriers; compute warps release a slot by arriving on empty[].
+__device__ __forceinline__ double4a ldg256(const double *p)
+{
+  double4a v;
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void stg256(double *p, const double4a &v)
+{
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int kTravStages = 4;
+constexpr int kTravComputeWarps = 7;  // + 1 producer warp = 256 threads, 2 blocks/SM at 128 registers
+constexpr int kTravThreads = (kTravComputeWarps + 1) * 32;
+
+template <int NCATG>
+struct __align__(128) TravStage
+{
+  OpDev  op;  // 96 bytes
+  char   pad[128 - sizeof(OpDev)];
+  double M[2][NCATG * 64];  // per child: P[cat][i][j] (NCATG*16) or TP[cat][mask][i] (NCATG*64)
+};
+
+__device__ __forceinline__ bool all_one(const double4a &v)
+{
+  const long long one = 0x3FF0000000000000LL;
+  return (((__double_as_longlong(v.x) ^ one) | (__double_as_longlong(v.y) ^ one) | (__double_as_longlong(v.z) ^ one) |
+           (__double_as_longlong(v.w) ^ one)) == 0);
+}
+
+// operands of one update -> per-child conditional vectors uA, uB, the all-ones flag and the scaler sum
+template <int NCATG, int U, int KA, int KB>
+__device__ __forceinline__ void trav_operands(const TravStage<NCATG> &stg, int cat, const long long (&off4)[U],
+                                              const int (&sidx)[U], const double4a (&prev_o)[U],
+                                              const int (&prev_sc)[U], const double4a (&slot_v)[U],
+                                              const int (&slot_sc)[U], const uint32_t (&mA)[U],
+                                              const uint32_t (&mB)[U], double (&uA)[U][4], double (&uB)[U][4],
+                                              bool (&ones)[U], int (&sc)[U])
+{
+  double4a late_v[U];
+  if (KB == kSrcLate)
+  {
+    const double *c2 = stg.op.c2;
+    const int    *s2 = stg.op.s2;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      late_v[u] = ldg256(c2 + off4[u]);
+      sc[u] = s2[sidx[u]];
+    }
+  }
+  else
+  {
+#pragma unroll
+    for (int u = 0; u < U; ++u) sc[u] = 0;
+  }
+  // ---- child A
+  if (KA == kSrcTip)
+  {
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      const double *t = stg.M[0] + (cat * 16 + (int)mA[u]) * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) uA[u][i] = t[i];
+      ones[u] = (mA[u] == (uint32_t)kTipRowAllOnes);
+    }
+  }
+  else
+  {
+    double p[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) p[q] = stg.M[0][cat * 16 + q];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      const double4a &v = (KA == kSrcFwd) ? prev_o[u] : slot_v[u];
+      ones[u] = all_one(v);
+      matvec4(p, v, uA[u]);
+      sc[u] += (KA == kSrcFwd) ? prev_sc[u] : slot_sc[u];
+    }
+  }
+  // ---- child B
+  if (KB == kSrcTip)
+  {
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      const double *t = stg.M[1] + (cat * 16 + (int)mB[u]) * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) uB[u][i] = t[i];
+      ones[u] = ones[u] && (mB[u] == (uint32_t)kTipRowAllOnes);
+    }
+  }
+  else
+  {
+    double p[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) p[q] = stg.M[1][cat * 16 + q];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      const double4a &v = (KB == kSrcSlot) ? slot_v[u] : late_v[u];
+      ones[u] = ones[u] && all_one(v);
+      matvec4(p, v, uB[u]);
+      if (KB == kSrcSlot) sc[u] += slot_sc[u];
+    }
+  }
+}
+
+template <int NCATG, int UMAX>
+__global__ void __launch_bounds__(kTravThreads, 2)
+    k_traverse_dna(const OpDev *__restrict__ ops, int n_ops, int npat, int tile_sites, int n_tiles,
+                   const double *__restrict__ wght, const uint32_t *__restrict__ tipmask, int apply_scaling)
+{
+  static_assert(NCATG == 1 || NCATG == 2 || NCATG == 4 || NCATG == 8, "NCATG must divide the warp");
+  constexpr int      S = kTravStages;
+  constexpr int      CT = kTravComputeWarps * 32;  // compute threads
+  constexpr uint32_t PB = NCATG * 16 * sizeof(double);   // P
+  constexpr uint32_t TB = NCATG * 64 * sizeof(double);   // tip table
+  __shared__ TravStage<NCATG>       st[S];
+  __shared__ __align__(8) uint64_t full[S], empty[S];
+  __shared__ uint32_t               smask[256];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0)
+  {
+    for (int s = 0; s < S; ++s)
+    {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kTravComputeWarps);
+    }
+  }
+  for (int i = tid; i < 256; i += kTravThreads) smask[i] = (uint32_t)tip_row4((int)tipmask[i]);  // code -> table row
+  __syncthreads();
+
+  const int       rounds = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const long long total_it = (long long)rounds * n_ops;
+
+  if (warp == kTravComputeWarps)
+  {  // ---------------- producer warp: descriptor + the two matrices of every update, S updates ahead.
+    // The 32 lanes read the matrix pointers / kinds of 32 consecutive updates in one go, so the
+    // issuing lane never waits on a dependent global load per update.
+    for (long long base = 0; base < total_it; base += 32)
+    {
+      const long long    my = base + lane;
+      unsigned long long m1 = 0, m2 = 0;
+      int                kd = 0;
+      if (my < total_it)
+      {
+        const OpDev *o = ops + (my % n_ops);
+        m1 = (unsigned long long)o->P1;
+        m2 = (unsigned long long)o->P2;
+        kd = o->flags;
+      }
+      const int cnt = (int)min((long long)32, total_it - base);
+      for (int j = 0; j < cnt; ++j)
+      {
+        const unsigned long long a1 = __shfl_sync(0xffffffffu, m1, j), a2 = __shfl_sync(0xffffffffu, m2, j);
+        const int                kind = __shfl_sync(0xffffffffu, kd, j);
+        if (lane == 0)
+        {
+          const long long it = base + j;
+          const int       s = (int)(it % S);
+          const uint32_t  ph = (uint32_t)((it / S) & 1);
+          mbar_wait(&empty[s], ph ^ 1u);
+          const uint32_t b1 = ((kind & 3) == kSrcTip) ? TB : PB;
+          const uint32_t b2 = ((kind >> 2) == kSrcTip) ? TB : PB;
+          mbar_expect_tx(&full[s], (uint32_t)sizeof(OpDev) + b1 + b2);
+          tma_bulk_g2s(&st[s].op, ops + (it % n_ops), (uint32_t)sizeof(OpDev), &full[s]);
+          tma_bulk_g2s(st[s].M[0], (const void *)a1, b1, &full[s]);
+          tma_bulk_g2s(st[s].M[1], (const void *)a2, b2, &full[s]);
+        }
+        __syncwarp();
+      }
+    }
+    return;
+  }
+
+  // ---------------- compute warps
+  // lane -> (site, category): the SW = 32/NCATG lanes of a category group read the same P rows
+  // (shared-memory broadcast), the NCATG groups of a warp cover the same SW sites.
+  constexpr int SW = 32 / NCATG;
+  const int     cat = lane / SW;
+  const double big = two_to_large(), small = inv_two_to_large();
+  long long    it = 0;
+  for (int r = 0; r < rounds; ++r)
+  {
+    const int tile = (int)blockIdx.x + r * (int)gridDim.x;
+    const int base_site = tile * tile_sites;
+    const int n_sites = min(tile_sites, npat - base_site);
+    const int n_items = n_sites * NCATG;
+    int       sidx[UMAX];
+    long long off4[UMAX];  // element offset of the item's 4 states
+    bool      live[UMAX];
+#pragma unroll
+    for (int u = 0; u < UMAX; ++u)
+    {
+      const int ls = (u * kTravComputeWarps + warp) * SW + (lane % SW);  // site within the tile
+      const int lc = ls < n_sites ? ls : n_sites - 1;
+      sidx[u] = base_site + lc;
+      off4[u] = ((long long)sidx[u] * NCATG + cat) * 4;
+      live[u] = (ls < n_sites) && (wght[sidx[u]] > DBL_MIN);  // avx.c:399
+    }
+    (void)n_items;
+
+    double4a prev_o[UMAX];  // result of the previous update (FWD operand of the next one)
+    int      prev_sc[UMAX];
+    double4a slot_v[UMAX];  // prefetched CLV operand
+    int      slot_sc[UMAX];
+    uint32_t mA[UMAX], mB[UMAX];  // prefetched tip masks
+#pragma unroll
+    for (int u = 0; u < UMAX; ++u)
+    {
+      prev_o[u].x = prev_o[u].y = prev_o[u].z = prev_o[u].w = 0.0;
+      slot_v[u] = prev_o[u];
+      prev_sc[u] = slot_sc[u] = 0;
+      mA[u] = mB[u] = 0u;
+    }
+
+    // operand prefetch for the update staged in `sn`
+#define PLK_FETCH(sn)                                                                  \
+  {                                                                                    \
+    const OpDev &on = st[sn].op;                                                       \
+    const int    kn = on.flags, ka = kn & 3, kb = kn >> 2;                             \
+    nx_kind = kn;                                                                      \
+    nx_dst = on.dst;                                                                   \
+    nx_dst_scale = on.dst_scale;                                                       \
+    if (ka == kSrcSlot || kb == kSrcSlot)                                              \
+    {                                                                                  \
+      const double *lp = (ka == kSrcSlot) ? on.c1 : on.c2;                             \
+      const int    *ls = (ka == kSrcSlot) ? on.s1 : on.s2;                             \
+      _Pragma("unroll") for (int u = 0; u < UMAX; ++u)                                 \
+      {                                                                                \
+        slot_v[u] = ldg256(lp + off4[u]);                                              \
+        slot_sc[u] = ls[sidx[u]];                                                      \
+      }                                                                                \
+    }                                                                                  \
+    if (ka == kSrcTip)                                                                 \
+    {                                                                                  \
+      const uint8_t *tp = on.t1;                                                       \
+      _Pragma("unroll") for (int u = 0; u < UMAX; ++u) mA[u] = smask[tp[sidx[u]]];     \
+    }                                                                                  \
+    if (kb == kSrcTip)                                                                 \
+    {                                                                                  \
+      const uint8_t *tp = on.t2;                                                       \
+      _Pragma("unroll") for (int u = 0; u < UMAX; ++u) mB[u] = smask[tp[sidx[u]]];     \
+    }                                                                                  \
+  }
+
+    int     nx_kind = 0;
+    double *nx_dst = nullptr;
+    int    *nx_dst_scale = nullptr;
+    {
+      const int      s0 = (int)(it % S);
+      const uint32_t ph0 = (uint32_t)((it / S) & 1);
+      mbar_wait(&full[s0], ph0);
+      PLK_FETCH(s0)
+    }
+
+    for (int k = 0; k < n_ops; ++k, ++it)
+    {
+      const int                s = (int)(it % S);
+      const TravStage<NCATG> &stg = st[s];
+      const int                kind = nx_kind;
+      double *const            dst = nx_dst;
+      int *const               dst_scale = nx_dst_scale;
+
+      double uA[UMAX][4], uB[UMAX][4];
+      bool   ones[UMAX];
+      int    sc[UMAX];
+#define PLK_OPERANDS(KA, KB) \
+  trav_operands<NCATG, UMAX, KA, KB>(stg, cat, off4, sidx, prev_o, prev_sc, slot_v, slot_sc, mA, mB, uA, uB, ones, sc)
+      switch (kind)
+      {
+      case (kSrcFwd | (kSrcTip << 2)): PLK_OPERANDS(kSrcFwd, kSrcTip); break;
+      case (kSrcFwd | (kSrcSlot << 2)): PLK_OPERANDS(kSrcFwd, kSrcSlot); break;
+      case (kSrcTip | (kSrcTip << 2)): PLK_OPERANDS(kSrcTip, kSrcTip); break;
+      case (kSrcSlot | (kSrcTip << 2)): PLK_OPERANDS(kSrcSlot, kSrcTip); break;
+      default: PLK_OPERANDS(kSrcSlot, kSrcLate); break;
+      }
+#undef PLK_OPERANDS
+
+      // the operands of this update are consumed: prefetch those of the next one
+      if (k + 1 < n_ops)
+      {
+        const int      sn = (int)((it + 1) % S);
+        const uint32_t phn = (uint32_t)(((it + 1) / S) & 1);
+        mbar_wait(&full[sn], phn);
+        PLK_FETCH(sn)
+      }
+
+#pragma unroll
+      for (int u = 0; u < UMAX; ++u)
+      {
+        double4a o;
+        if (ones[u])
+        {  // avx.c:575-587
+          o.x = o.y = o.z = o.w = 1.0;
+        }
+        else
+        {
+          o.x = uA[u][0] * uB[u][0];
+          o.y = uA[u][1] * uB[u][1];
+          o.z = uA[u][2] * uB[u][2];
+          o.w = uA[u][3] * uB[u][3];
+        }
+        // avx.c:498-510
+        double mx = fmax(fmax(o.x, o.y), fmax(o.z, o.w));
+#pragma unroll
+        for (int d = SW; d < 32; d <<= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+        int sco = sc[u];
+        if (mx < small && apply_scaling)
+        {
+          o.x *= big;
+          o.y *= big;
+          o.z *= big;
+          o.w *= big;
+          sco += kLarge;
+        }
+        if (live[u])
+        {
+          stg256(dst + off4[u], o);
+          if (cat == 0) dst_scale[sidx[u]] = sco;
+        }
+        prev_o[u] = o;
+        prev_sc[u] = sco;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+#undef PLK_FETCH
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 generic: thread per site, any ns <= 32, any ncatg <= 16.  Same arithmetic order.
+__device__ __forceinline__ double child_dot(const double *__restrict__ Prow, const double *__restrict__ v, uint32_t mask,
+                                            bool internal, int ns)
+{
+  if (internal)
+  {
+    double a = Prow[0] * v[0];
+    for (int j = 1; j < ns; ++j) a = fma(Prow[j], v[j], a);
+    return a;
+  }
+  double a = (mask & 1u) ? Prow[0] : 0.0;
+  for (int j = 1; j < ns; ++j)
+    if ((mask >> j) & 1u) a = a + Prow[j];
+  return a;
+}
+
+__global__ void __launch_bounds__(128)
+    k_partial_generic(const OpDev *__restrict__ ops, int blocks_per_op, int npat, int ns, int ncatg,
+                      const double *__restrict__ wght, const uint32_t *__restrict__ tipmask, int apply_scaling)
+{
+  const OpDev    op = ops[blockIdx.x / blocks_per_op];
+  const int      blk = blockIdx.x % blocks_per_op;
+  const int      ncns = ncatg * ns, nn = ns * ns;
+  const uint32_t full = (ns >= 32) ? 0xffffffffu : ((1u << ns) - 1u);
+  const double   big = two_to_large(), small = inv_two_to_large();
+
+  for (int site = blk * blockDim.x + threadIdx.x; site < npat; site += blocks_per_op * blockDim.x)
+  {
+    if (!(wght[site] > DBL_MIN)) continue;
+    const double  *v1 = op.c1 ? op.c1 + (size_t)site * ncns : nullptr;
+    const double  *v2 = op.c2 ? op.c2 + (size_t)site * ncns : nullptr;
+    const uint32_t m1 = op.c1 ? 0u : tipmask[op.t1[site]];
+    const uint32_t m2 = op.c2 ? 0u : tipmask[op.t2[site]];
+    double        *out = op.dst + (size_t)site * ncns;
+    double         largest = -DBL_MAX;
+    for (int c = 0; c < ncatg; ++c)
+    {
+      const double *a1 = v1 ? v1 + c * ns : nullptr;
+      const double *a2 = v2 ? v2 + c * ns : nullptr;
+      bool          ones = (v1 ? true : m1 == full) && (v2 ? true : m2 == full);
+      if (ones && v1)
+        for (int j = 0; j < ns; ++j) ones = ones && (a1[j] == 1.0);
+      if (ones && v2)
+        for (int j = 0; j < ns; ++j) ones = ones && (a2[j] == 1.0);
+      for (int i = 0; i < ns; ++i)
+      {
+        double o;
+        if (ones)
+          o = 1.0;
+        else
+          o = child_dot(op.P1 + c * nn + i * ns, a1, m1, v1 != nullptr, ns) *
+              child_dot(op.P2 + c * nn + i * ns, a2, m2, v2 != nullptr, ns);
+        out[c * ns + i] = o;
+        largest = fmax(largest, o);
+      }
+    }
+    int sc = (op.s1 ? op.s1[site] : 0) + (op.s2 ? op.s2[site] : 0);
+    if (largest < small && apply_scaling)
+    {
+      for (int k = 0; k < ncns; ++k) out[k] *= big;
+      sc += kLarge;
+    }
+    op.dst_scale[site] = sc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Block reduction of up to 2 running sums, deterministic: fixed shuffle tree, fixed warp order.
+template <int NV>
+__device__ __forceinline__ void block_reduce_store(double (&v)[NV], int warn, double *partials, int *warn_out)
+{
+  __shared__ double sred[NV][32];
+  __shared__ int    swarn;
+  if (threadIdx.x == 0) swarn = 0;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], d);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0)
+#pragma unroll
+    for (int k = 0; k < NV; ++k) sred[k][wid] = v[k];
+  if (warn) atomicOr(&swarn, 1);
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    const int nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+    {
+      double s = 0.0;
+      for (int w = 0; w < nw; ++w) s += sred[k][w];
+      partials[(size_t)blockIdx.x * NV + k] = s;
+    }
+    if (swarn) atomicOr(warn_out, 1);
+  }
+}
+
+// result block shared with the host through mapped pinned memory
+struct ResultHost
+{
+  double            val[2];
+  int               warn;
+  int               pad;
+  unsigned long long seq;
+};
+
+// second stage: sums the per-block partials in index order, publishes to the host
+__global__ void k_reduce_final(const double *__restrict__ partials, int nblocks, int nv, double *dev_out,
+                               int *warn_flag, volatile ResultHost *host_out, unsigned long long seq, int publish)
+{
+  __shared__ double s[2][256];
+  for (int k = 0; k < nv; ++k)
+  {
+    double a = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += 256) a += partials[(size_t)b * nv + k];
+    s[k][threadIdx.x] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    double r[2] = {0.0, 0.0};
+    for (int k = 0; k < nv; ++k)
+      for (int t = 0; t < 256; ++t) r[k] += s[k][t];
+    dev_out[0] = r[0];
+    dev_out[1] = r[1];
+    const int w = *warn_flag;
+    *warn_flag = 0;
+    if (publish)
+    {
+      host_out->val[0] = r[0];
+      host_out->val[1] = r[1];
+      host_out->warn = w;
+      __threadfence_system();
+      host_out->seq = seq;
+    }
+    else
+    {
+      dev_out[2] = (double)w;  // summed across ranks with the values: > 0 means some rank warned
+    }
+  }
+}
+
+// publishes an (all-reduced) device result to the host
+__global__ void k_publish(const double *dev_out, volatile ResultHost *host_out, unsigned long long seq)
+{
+  host_out->val[0] = dev_out[0];
+  host_out->val[1] = dev_out[1];
+  host_out->warn = dev_out[2] > 0.0 ? 1 : 0;
+  __threadfence_system();
+  host_out->seq = seq;
+}
+
+// +I term, lk.c:1226-1273
+__device__ __forceinline__ double invariant_lk(int fact, int invar_state, const double *pi, bool *overflow)
+{
+  double v = 0.0;
+  *overflow = false;
+  if (invar_state > -1)
+  {
+    int e = fact;
+    v = pi[invar_state];
+    do
+    {
+      const int piece = e < 63 ? e : 63;
+      v *= (double)(1ULL << piece);
+      e -= piece;
+    } while (e != 0);
+    if (isinf(v)) *overflow = true;
+  }
+  return v;
+}
+
+// horizontal sum in the order of AVX_Vect_Norm (avx.c:281-289)
+__device__ __forceinline__ double hsum4(double x0, double x1, double x2, double x3) { return (x0 + x2) + (x1 + x3); }
+
+// ------------------------------------------------------------------------------------------------
+// K2: thread per site.
+__global__ void __launch_bounds__(128)
+    k_edge_lnl(SideDev left, SideDev rght, const double *__restrict__ P, const ModelDev *__restrict__ mod, int npat,
+               int ns, int ncatg, const double *__restrict__ wght, const short *__restrict__ invar,
+               const uint32_t *__restrict__ tipmask, double *__restrict__ site_lnl, double *__restrict__ site_lk_out,
+               double *__restrict__ site_lk_cat, int *__restrict__ fact_sum_scale, double *partials, int *warn_out)
+{
+  const int    ncns = ncatg * ns, nn = ns * ns;
+  const double *pi = mod->pi;
+  double       acc[1] = {0.0};
+  int          warn = 0;
+
+  for (int site = blockIdx.x * blockDim.x + threadIdx.x; site < npat; site += gridDim.x * blockDim.x)
+  {
+    const double w = wght[site];
+    if (!(w > DBL_MIN)) continue;  // lk.c:632
+    const uint32_t lm = left.clv ? 0u : tipmask[left.tip[site]];
+    const uint32_t rm = rght.clv ? 0u : tipmask[rght.tip[site]];
+    const bool     unamb = (!rght.clv) && (__popc(rm) == 1);  // lk.c:614-621
+    const int      st = unamb ? (__ffs(rm) - 1) : -1;
+    double         site_lk = 0.0;
+
+    for (int c = 0; c < ncatg; ++c)
+    {
+      const double *Pc = P + (size_t)c * nn;
+      const double *L = left.clv ? left.clv + (size_t)site * ncns + c * ns : nullptr;
+      const double *R = rght.clv ? rght.clv + (size_t)site * ncns + c * ns : nullptr;
+      double        lk;
+      if ((ns & 3) == 0)
+      {  // order of AVX_Lk_Core_One_Class_No_Eigen_Lr (avx.c:110-215)
+        if (unamb)
+        {
+          double q[4] = {0.0, 0.0, 0.0, 0.0};
+          for (int b = 0; b < ns; b += 4)
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+            {
+              const double lv = L ? L[b + t] : (double)((lm >> (b + t)) & 1u);
+              q[t] = q[t] + Pc[st * ns + b + t] * lv;
+            }
+          lk = pi[st] * hsum4(q[0], q[1], q[2], q[3]);
+        }
+        else
+        {
+          lk = 0.0;
+          for (int b = 0; b < ns; b += 4)
+          {
+            double x[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+            {
+              const int    k = b + t;
+              const double rv = R ? R[k] : (double)((rm >> k) & 1u);
+              double       a = 0.0;
+              for (int l = 0; l < ns; ++l)
+              {
+                const double lv = L ? L[l] : (double)((lm >> l) & 1u);
+                a = fma(Pc[k * ns + l], lv, a);
+              }
+              x[t] = a * (rv * pi[k]);
+            }
+            lk = lk + hsum4(x[0], x[1], x[2], x[3]);
+          }
+        }
+      }
+      else
+      {  // scalar order, lk.c:1185-1218
+        lk = 0.0;
+        if (unamb)
+        {
+          double sum = 0.0;
+          for (int l = 0; l < ns; ++l) sum = sum + Pc[st * ns + l] * (L ? L[l] : (double)((lm >> l) & 1u));
+          lk = sum * pi[st];
+        }
+        else
+          for (int k = 0; k < ns; ++k)
+          {
+            const double rv = R ? R[k] : (double)((rm >> k) & 1u);
+            if (rv > 0.0)
+            {
+              double sum = 0.0;
+              for (int l = 0; l < ns; ++l) sum = sum + Pc[k * ns + l] * (L ? L[l] : (double)((lm >> l) & 1u));
+              lk = lk + sum * pi[k] * rv;
+            }
+          }
+      }
+      site_lk_cat[(size_t)site * ncatg + c] = lk;  // lk.c:2801
+      site_lk = site_lk + lk * mod->probs[c];        // lk.c:818
+    }
+
+    int fact = (left.scale ? left.scale[site] : 0) + (rght.scale ? rght.scale[site] : 0);  // lk.c:2781-2791
+    if (mod->invar_flag)
+    {  // lk.c:820-842
+      bool   ovf;
+      double inv = invariant_lk(fact, invar[site], pi, &ovf);
+      if (ovf)
+      {
+        fact = 0;
+        inv = invariant_lk(0, invar[site], pi, &ovf);
+        site_lk = inv * mod->pinv;
+      }
+      else
+        site_lk = site_lk * (1. - mod->pinv) + inv * mod->pinv;
+    }
+    if (site_lk < DBL_MIN)
+    {  // lk.c:847-851
+      site_lk = DBL_MIN;
+      warn = 1;
+    }
+    const double lsl = log(site_lk) - kLog2 * fact;  // lk.c:854
+    site_lnl[site] = lsl;
+    site_lk_out[site] = exp(lsl);  // lk.c:857
+    fact_sum_scale[site] = fact;
+    acc[0] += w * lsl;  // lk.c:856
+  }
+  block_reduce_store<1>(acc, warn, partials, warn_out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: thread per (site, category).
+__global__ void __launch_bounds__(128)
+    k_eigen_lr(SideDev left, SideDev rght, const ModelDev *__restrict__ mod, int npat, int ns, int ncatg,
+               const double *__restrict__ wght, const uint32_t *__restrict__ tipmask, double *__restrict__ dot_prod,
+               int *__restrict__ fact_sum_scale)
+{
+  const int       ncns = ncatg * ns;
+  const long long total = (long long)npat * ncatg;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x)
+  {
+    const int site = (int)(g / ncatg), c = (int)(g % ncatg);
+    if (c == 0) fact_sum_scale[site] = (left.scale ? left.scale[site] : 0) + (rght.scale ? rght.scale[site] : 0);
+    if (!(wght[site] > DBL_MIN)) continue;  // lk.c:1082
+    const double  *L = left.clv ? left.clv + (size_t)site * ncns + c * ns : nullptr;
+    const double  *R = rght.clv ? rght.clv + (size_t)site * ncns + c * ns : nullptr;
+    const uint32_t lm = L ? 0u : tipmask[left.tip[site]];
+    const uint32_t rm = R ? 0u : tipmask[rght.tip[site]];
+    double        *o = dot_prod + (size_t)site * ncns + c * ns;
+    for (int i = 0; i < ns; ++i)
+    {  // avx.c:79-84: left_i = sum_j U[j][i] (L_j pi_j), rght_i = sum_j V[i][j] R_j, first term a product
+      double a, b;
+      {
+        const double l0 = (L ? L[0] : (double)(lm & 1u)) * mod->pi[0];
+        const double r0 = R ? R[0] : (double)(rm & 1u);
+        a = mod->U[i] * l0;
+        b = mod->V[i * ns] * r0;
+      }
+      for (int j = 1; j < ns; ++j)
+      {
+        const double lj = (L ? L[j] : (double)((lm >> j) & 1u)) * mod->pi[j];
+        const double rj = R ? R[j] : (double)((rm >> j) & 1u);
+        a = fma(mod->U[j * ns + i], lj, a);
+        b = fma(mod->V[i * ns + j], rj, b);
+      }
+      o[i] = a * b;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: thread per site.  expl = (E,D) interleaved per category like tree->expl (lk.c:717-725).
+__global__ void __launch_bounds__(128)
+    k_lnl_dlnl(const double *__restrict__ dot_prod, const int *__restrict__ fact_sum_scale,
+               const ModelDev *__restrict__ mod, double l, int with_derivative, int npat, int ns, int ncatg,
+               const double *__restrict__ wght, const short *__restrict__ invar, double *__restrict__ site_lnl,
+               double *partials, int *warn_out)
+{
+  __shared__ double sE[kMaxCatg * kMaxNs], sD[kMaxCatg * kMaxNs];
+  const int         ncns = ncatg * ns;
+  for (int t = threadIdx.x; t < ncns; t += blockDim.x)
+  {
+    const int c = t / ns, i = t % ns;
+    double    len, rr = mod->rates[c];
+    if (with_derivative)
+    {  // lk.c:690-705
+      rr = rr * mod->br_len_mult;
+      len = l * rr;
+    }
+    else
+    {  // lk.c:596-600
+      len = fmax(0.0, l) * mod->rates[c];
+      len = len * mod->br_len_mult;
+    }
+    if (len < mod->l_min)
+      len = mod->l_min;
+    else if (len > mod->l_max)
+      len = mod->l_max;
+    const double e = exp(mod->lambda[i] * len);
+    sE[t] = e;
+    sD[t] = e * mod->lambda[i] * rr;
+  }
+  __syncthreads();
+
+  double acc[2] = {0.0, 0.0};
+  int    warn = 0;
+  for (int site = blockIdx.x * blockDim.x + threadIdx.x; site < npat; site += gridDim.x * blockDim.x)
+  {
+    const double w = wght[site];
+    if (!(w > DBL_MIN)) continue;
+    const double *dp = dot_prod + (size_t)site * ncns;
+    int           fact = fact_sum_scale[site];
+    double        lk = 0.0, dlk = 0.0;
+    for (int c = 0; c < ncatg; ++c)
+    {
+      double cl, cd = 0.0;
+      if ((ns & 3) == 0)
+      {
+        if (with_derivative)
+        {  // avx.c:250-276: even/odd states accumulate separately with FMAs, then add
+          double le = 0.0, lo = 0.0, de = 0.0, dd = 0.0;
+          for (int i = 0; i < ns; i += 2)
+          {
+            le = fma(dp[c * ns + i], sE[c * ns + i], le);
+            de = fma(dp[c * ns + i], sD[c * ns + i], de);
+            lo = fma(dp[c * ns + i + 1], sE[c * ns + i + 1], lo);
+            dd = fma(dp[c * ns + i + 1], sD[c * ns + i + 1], dd);
+          }
+          cl = le + lo;
+          cd = de + dd;
+        }
+        else
+        {  // avx.c:220-245
+          double q[4] = {0.0, 0.0, 0.0, 0.0};
+          for (int b = 0; b < ns; b += 4)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) q[t] = q[t] + dp[c * ns + b + t] * sE[c * ns + b + t];
+          cl = hsum4(q[0], q[1], q[2], q[3]);
+        }
+      }
+      else
+      {  // lk.c:1157-1180
+        cl = 0.0;
+        for (int i = 0; i < ns; ++i)
+        {
+          cl = cl + dp[c * ns + i] * sE[c * ns + i];
+          cd = cd + dp[c * ns + i] * sD[c * ns + i];
+        }
+      }
+      lk = lk + cl * mod->probs[c];
+      dlk = dlk + cd * mod->probs[c];
+    }
+    if (mod->invar_flag)
+    {
+      bool   ovf;
+      double inv = invariant_lk(fact, invar[site], mod->pi, &ovf);
+      if (with_derivative)
+      {  // lk.c:1005-1025
+        if (ovf)
+        {
+          lk = inv * mod->pinv;
+          dlk = 0.0;
+        }
+        else
+        {
+          lk = lk * (1. - mod->pinv) + inv * mod->pinv;
+          dlk = dlk * (1. - mod->pinv);
+        }
+      }
+      else
+      {  // lk.c:910-931
+        if (ovf)
+        {
+          fact = 0;
+          inv = invariant_lk(0, invar[site], mod->pi, &ovf);
+          lk = inv * mod->pinv;
+        }
+        else
+          lk = lk * (1. - mod->pinv) + inv * mod->pinv;
+      }
+    }
+    if (lk < DBL_MIN)
+    {
+      lk = DBL_MIN;
+      warn = 1;
+    }
+    const double lsl = log(lk) - kLog2 * fact;
+    if (!with_derivative) site_lnl[site] = lsl;  // Lk_Core_Eigen_Lr writes c_lnL_sorted (lk.c:945); dLk does not
+    acc[0] += w * lsl;
+    acc[1] += w * (dlk / lk);
+  }
+  block_reduce_store<2>(acc, warn, partials, warn_out);
+}
+
+}  // namespace plk

@@ -51,11 +51,11 @@ class LkTree:
         self._queue: List[PartialOp] = []
         self._eigen_edge = -1
         self.n_flush = 0
-        eng.set_weights(patterns.wght, patterns.invar)
-        eng.set_tip_table(patterns.table())
+        engine.set_weights(patterns.wght, patterns.invar)
+        engine.set_tip_table(patterns.table())
         for i in range(tree.n_otu):
-            eng.set_tip_codes(i, patterns.codes[i])
-        eng.set_model(model)
+            engine.set_tip_codes(i, patterns.codes[i])
+        engine.set_model(model)
 
     # ---------------------------------------------------------------- flags (utilities.c:11614+)
     def Set_Both_Sides(self, yesno):

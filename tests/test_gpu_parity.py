@@ -1,0 +1,195 @@
+"""Parity tests proper: the CUDA engine, called through the C ABI (libphyml_b200.so via ctypes),
+against (a) the golden arrays dumped from the unmodified reference and (b) the CPU oracle on
+seeded synthetic inputs.  Need a B200: marked gpu."""
+import numpy as np
+import pytest
+
+import parity_checks as pc
+from golden_case import ALL_CASES, GoldenCase
+from oracle_backend import OracleBackend
+
+from phyml_b200 import alignment, model as pmodel
+from phyml_b200.engine import Engine
+from phyml_b200.lk import LkTree
+from phyml_b200.tree import Tree
+
+pytestmark = pytest.mark.gpu
+
+DNA_CASES = [c for c in ALL_CASES if "aa" not in c and "proteic" not in c]
+
+
+def make(case):
+    c = GoldenCase(case)
+    eng = Engine(c.n_otu, c.P, c.ns, c.ncatg, c.tree.n_clv_handles, c.tree.n_edges)
+    c.upload(eng)
+    return c, eng
+
+
+@pytest.mark.parametrize("case", ALL_CASES)
+def test_pmat(case):
+    """K0 on device vs the reference's b->Pij_rr (exp() differs by <= 1 ulp from libm)."""
+    c, eng = make(case)
+    pc.check_pmat(c, eng, atol=2e-14)
+
+
+@pytest.mark.parametrize("case", ALL_CASES)
+def test_full_traversal_exact(case):
+    """K1 reproduces the reference's AVX+FMA arithmetic order: with the reference's P-matrices every
+    CLV (post- and pre-order) and every scaler must be BIT-IDENTICAL to the reference's."""
+    c, eng = make(case)
+    pc.check_full_traversal(c, eng, clv_rtol=0, exact=True)
+
+
+@pytest.mark.parametrize("case", ALL_CASES)
+def test_lnl_end_to_end(case):
+    """tips + branch lengths + eigen system in, lnL out: <= 1e-12 relative (target 1e-9)."""
+    c, eng = make(case)
+    pc.check_lnl_end_to_end(c, eng, rtol=1e-12)
+
+
+@pytest.mark.parametrize("case", ALL_CASES)
+def test_lnl_at_every_edge(case):
+    c, eng = make(case)
+    pc.check_lnl_every_edge(c, eng, rtol=1e-12)
+
+
+@pytest.mark.parametrize("case", ALL_CASES)
+def test_eigen_lr_and_dlk(case):
+    c, eng = make(case)
+    pc.check_eigen_lr_and_dlk(c, eng, row_tol=1e-13, golden_pmat=True)
+    c, eng = make(case)
+    pc.check_eigen_lr_and_dlk(c, eng, row_tol=1e-9)   # device-computed P: exp() differs from libm by <= 1 ulp
+
+
+def _synthetic(ns, n_taxa, n_sites, seed, ambiguity, ncatg=4, pinv=0.0, mean_bl=0.1):
+    tree = Tree.random(n_taxa, seed=seed, mean_bl=mean_bl)
+    if ns == 4:
+        m = pmodel.gtr(alpha=0.5, ncatg=ncatg, pinv=pinv)
+    else:
+        m = pmodel.lg_from_fixture(alpha=0.5, ncatg=ncatg)
+    codes = alignment.simulate(tree, m, n_sites, seed=seed + 1, ambiguity=ambiguity)
+    pat = alignment.compress(codes, ns)
+    return tree, m, pat
+
+
+@pytest.mark.parametrize("ns,n_taxa,n_sites,ncatg,pinv,amb,mean_bl", [
+    (4, 12, 3000, 4, 0.0, 0.02, 0.1),
+    (4, 40, 5000, 4, 0.1, 0.0, 0.1),
+    (4, 300, 257, 4, 0.0, 0.03, 0.4),     # deep: rescaling fires
+    (4, 16, 1001, 1, 0.0, 0.0, 0.1),      # ncatg = 1
+    (4, 16, 1001, 8, 0.0, 0.05, 0.1),     # ncatg = 8
+    (4, 16, 999, 6, 0.0, 0.05, 0.1),      # ncatg not a power of two -> generic kernel
+    (20, 10, 700, 4, 0.0, 0.02, 0.1),
+    (20, 30, 301, 2, 0.0, 0.0, 0.2),
+])
+def test_engine_vs_oracle_synthetic(ns, n_taxa, n_sites, ncatg, pinv, amb, mean_bl):
+    """CUDA vs oracle through the reference-named host interface (LkTree): lnL, every CLV, scalers,
+    dLk, on seeded synthetic data incl. ragged sizes (pattern counts not multiples of the tile)."""
+    tree, m, pat = _synthetic(ns, n_taxa, n_sites, 3, amb, ncatg, pinv, mean_bl)
+    args = (tree.n_otu, pat.n_pattern, ns, ncatg, tree.n_clv_handles, tree.n_edges)
+    gpu = LkTree(tree, pat, m, Engine(*args))
+    cpu = LkTree(tree, pat, m, OracleBackend(*args))
+    for t in (gpu, cpu):
+        t.Set_Both_Sides(1)
+    lg, lc = gpu.Lk(), cpu.Lk()
+    assert abs(lg - lc) <= 1e-12 * abs(lc)
+    for h in range(tree.n_clv_handles):
+        if h in cpu.eng.clv:
+            a, sa = gpu.eng.get_clv(h)
+            b, sb = cpu.eng.get_clv(h)
+            assert (sa == sb).all()
+            # device exp() vs libm exp() differ by <= 1 ulp; tiny CLV entries inherit the ABSOLUTE
+            # accuracy of near-zero P entries, so compare on the scale of each site
+            assert (np.abs(a - b) <= 1e-12 * np.abs(b).max(axis=(1, 2), keepdims=True)).all()
+            np.testing.assert_allclose(a, b, rtol=1e-6, atol=0)
+    e = tree.n_edges // 2
+    for t in (gpu, cpu):
+        t.Set_Update_Eigen_Lr(1)
+        t.Lk(e)
+        t.Set_Update_Eigen_Lr(0)
+    for l in (1e-9, 0.01, 0.3, 250.0):
+        rg, rc = gpu.dLk(l, e), cpu.dLk(l, e)
+        assert rg[0] == rc[0]
+        assert abs(rg[1] - rc[1]) <= 1e-12 * abs(rc[1])
+        assert abs(gpu.c_dlnL - cpu.c_dlnL) <= 1e-9 * max(1.0, abs(cpu.c_dlnL))
+
+
+def test_zero_weight_patterns_and_single_pattern():
+    """Edge cases of the reference's site loop: wght <= DBL_MIN patterns are skipped (bootstrap
+    zero weights, lk.c:1682) and a 1-pattern alignment works."""
+    tree, m, pat = _synthetic(4, 9, 400, 5, 0.05)
+    pat.wght[::3] = 0.0
+    args = (tree.n_otu, pat.n_pattern, 4, 4, tree.n_clv_handles, tree.n_edges)
+    gpu, cpu = LkTree(tree, pat, m, Engine(*args)), LkTree(tree, pat, m, OracleBackend(*args))
+    assert abs(gpu.Lk() - cpu.Lk()) <= 1e-12 * abs(cpu.c_lnL)
+    one = pat.shard(0, pat.n_pattern)
+    assert one.n_pattern == 1
+    args = (tree.n_otu, 1, 4, 4, tree.n_clv_handles, tree.n_edges)
+    one.wght[:] = 1.0
+    gpu, cpu = LkTree(tree, one, m, Engine(*args)), LkTree(tree, one, m, OracleBackend(*args))
+    assert abs(gpu.Lk() - cpu.Lk()) <= 1e-12 * abs(cpu.c_lnL)
+
+
+def test_pulley_principle_and_branch_opt():
+    """The reference's own runtime invariants as engine self-tests: Check_Lk_At_Given_Edge
+    (lk.c:2642) and monotone improvement under Br_Len_Opt (optimiz.c:656-661)."""
+    tree, m, pat = _synthetic(4, 25, 4000, 9, 0.01)
+    t = LkTree(tree, pat, m, Engine(tree.n_otu, pat.n_pattern, 4, 4, tree.n_clv_handles, tree.n_edges))
+    t.Set_Both_Sides(1)
+    t.Lk()
+    vals = t.Check_Lk_At_Given_Edge(tol=1e-6)
+    assert np.ptp(vals) <= 1e-9 * abs(vals[0])
+    before = t.Lk()
+    e = 7
+    tree.l[e] *= 5.0
+    worse = t.Lk()
+    after = t.Br_Len_Opt(e)
+    assert after >= worse and after >= before - 1e-6
+
+
+def test_sharded_partials_sum_to_full():
+    """Site sharding (section 8e): per-shard partial lnL sums to the full value, on one GPU."""
+    tree, m, pat = _synthetic(4, 20, 6000, 2, 0.02)
+    full = LkTree(tree, pat, m, Engine(tree.n_otu, pat.n_pattern, 4, 4, tree.n_clv_handles, tree.n_edges)).Lk()
+    tot = 0.0
+    for r in range(3):
+        sh = pat.shard(r, 3)
+        tot += LkTree(tree, sh, m, Engine(tree.n_otu, sh.n_pattern, 4, 4, tree.n_clv_handles, tree.n_edges)).Lk()
+    assert abs(tot - full) <= 1e-12 * abs(full)
+
+
+def test_large_config_properties():
+    """BASELINE config 2 at full size (100 taxa x 100 000 sites, GTR+G4): size-independent properties
+    instead of an oracle run -- pulley principle across edges, invariance of lnL to the rooting tip,
+    additivity over site shards, and agreement with the oracle on a 2 000-site prefix."""
+    tree, m, pat = _synthetic(4, 100, 100000, 1, 0.0)
+    t = LkTree(tree, pat, m, Engine(tree.n_otu, pat.n_pattern, 4, 4, tree.n_clv_handles, tree.n_edges))
+    t.Set_Both_Sides(1)
+    full = t.Lk()
+    vals = np.array([t.Lk(e) for e in range(0, tree.n_edges, 17)])
+    assert np.abs(vals - full).max() <= 1e-10 * abs(full)
+    tree.tip_root = 37
+    t.Set_Both_Sides(0)
+    assert abs(t.Lk() - full) <= 1e-10 * abs(full)
+    tree.tip_root = 0
+    sub = alignment.Patterns(4, np.ascontiguousarray(pat.codes[:, :2000]), pat.wght[:2000].copy(),
+                             pat.invar[:2000].copy(), pat.names, 2000)
+    args = (tree.n_otu, 2000, 4, 4, tree.n_clv_handles, tree.n_edges)
+    a = LkTree(tree, sub, m, Engine(*args)).Lk()
+    b = LkTree(tree, sub, m, OracleBackend(*args)).Lk()
+    assert abs(a - b) <= 1e-12 * abs(b)
+
+
+def test_error_paths():
+    from phyml_b200.engine import EngineError
+    from phyml_b200.tree import Side
+
+    eng = Engine(4, 10, 4, 4, 10, 5)
+    with pytest.raises(EngineError):
+        eng.edge_lnl(Side(clv=3), Side(tip=0), 0)       # CLV never written
+    with pytest.raises(EngineError):
+        eng.lnl_dlnl(0.1)                                 # dLk before Update_Eigen_Lr
+    with pytest.raises(EngineError):
+        eng.update_pmats([99], [0.1])                     # handle out of range
+    with pytest.raises(EngineError):
+        Engine(4, 10, 64, 4, 10, 5)                       # ns unsupported
