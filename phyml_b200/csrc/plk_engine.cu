@@ -77,6 +77,8 @@ struct plk_instance
   short    *d_invar = nullptr;
   uint32_t *d_tipmask = nullptr;
   uint8_t  *d_tipcodes = nullptr;
+  uint8_t  *d_tiprows = nullptr;   // ns == 4: codes translated to tip-table rows for the fused kernel
+  bool      tiprows_dirty = true;
   size_t    tip_stride = 0;
   ModelDev *d_model = nullptr;
   double   *d_pmat = nullptr;
@@ -359,6 +361,7 @@ int plk_create(const plk_config *cfg, plk_instance **out)
   CREATE_RC(dev_alloc(inst, &inst->d_invar, P));
   CREATE_RC(dev_alloc(inst, &inst->d_tipmask, 256));
   CREATE_RC(dev_alloc(inst, &inst->d_tipcodes, inst->tip_stride * cfg->n_tips));
+  if (cfg->ns == 4) CREATE_RC(dev_alloc(inst, &inst->d_tiprows, inst->tip_stride * cfg->n_tips));
   CREATE_RC(dev_alloc(inst, &inst->d_model, 1));
   CREATE_RC(dev_alloc(inst, &inst->d_pmat, inst->pmat_stride * cfg->n_pmat));
   CREATE_RC(dev_alloc(inst, &inst->d_site_lnl, P));
@@ -404,6 +407,7 @@ void plk_destroy(plk_instance *inst)
   cudaFree(inst->d_invar);
   cudaFree(inst->d_tipmask);
   cudaFree(inst->d_tipcodes);
+  cudaFree(inst->d_tiprows);
   cudaFree(inst->d_model);
   cudaFree(inst->d_pmat);
   cudaFree(inst->d_site_lnl);
@@ -451,6 +455,7 @@ static int upload_masks(plk_instance *inst)
   int   rc = stage_upload(inst, tmp, sizeof(tmp), &d);
   if (rc) return rc;
   CU_TRY(inst, cudaMemcpyAsync(inst->d_tipmask, d, sizeof(tmp), cudaMemcpyDeviceToDevice, inst->stream));
+  inst->tiprows_dirty = true;
   return PLK_OK;
 }
 
@@ -477,6 +482,7 @@ int plk_set_tip_codes(plk_instance *inst, int tip, const uint8_t *codes)
   ARG_CHECK(inst, tip >= 0 && tip < inst->cfg.n_tips && codes, "tip index out of range");
   CU_TRY(inst, cudaMemcpyAsync(inst->d_tipcodes + (size_t)tip * inst->tip_stride, codes, inst->cfg.n_patterns,
                                cudaMemcpyHostToDevice, inst->stream));
+  inst->tiprows_dirty = true;
   return PLK_OK;
 }
 
@@ -485,6 +491,7 @@ int plk_set_all_tip_codes(plk_instance *inst, const uint8_t *codes, size_t host_
   ARG_CHECK(inst, codes && host_stride >= (size_t)inst->cfg.n_patterns, "plk_set_all_tip_codes: bad arguments");
   CU_TRY(inst, cudaMemcpy2DAsync(inst->d_tipcodes, inst->tip_stride, codes, host_stride, inst->cfg.n_patterns,
                                  inst->cfg.n_tips, cudaMemcpyHostToDevice, inst->stream));
+  inst->tiprows_dirty = true;
   return PLK_OK;
 }
 
@@ -648,8 +655,7 @@ template <int NCATG, int UMAX>
 static int launch_traverse_t(plk_instance *inst, const OpDev *d_ops, int n_ops, int tile_sites, int n_tiles, int grid)
 {
   k_traverse_dna<NCATG, UMAX><<<grid, kTravThreads, 0, inst->stream>>>(d_ops, n_ops, inst->cfg.n_patterns, tile_sites,
-                                                                       n_tiles, inst->d_wght, inst->d_tipmask,
-                                                                       inst->apply_scaling);
+                                                                       n_tiles, inst->d_wght, inst->apply_scaling);
   inst->launches++;
   CU_TRY(inst, cudaGetLastError());
   return PLK_OK;
@@ -703,6 +709,15 @@ int plk_update_partials(plk_instance *inst, int n_ops, const plk_op *ops)
   const int  nclv = inst->cfg.n_clv;
   const int  nc = inst->cfg.ncatg;
   const bool fused = (inst->cfg.ns == 4) && (nc == 1 || nc == 2 || nc == 4 || nc == 8);
+  if (fused && inst->tiprows_dirty)
+  {
+    const size_t n = inst->tip_stride * inst->cfg.n_tips;
+    k_codes_to_rows<<<(unsigned)std::min<size_t>((n + 255) / 256, 4096), 256, 0, inst->stream>>>(
+        inst->d_tipcodes, inst->d_tiprows, n, inst->d_tipmask);
+    inst->launches++;
+    CU_TRY(inst, cudaGetLastError());
+    inst->tiprows_dirty = false;
+  }
   // dependency levels: an op runs after the last writer of each operand it reads, after the last
   // reader of the buffer it overwrites and after the last writer of that buffer (RAW, WAR, WAW)
   inst->lvl_write.assign(nclv, -1);
@@ -799,9 +814,17 @@ int plk_update_partials(plk_instance *inst, int n_ops, const plk_op *ops)
         d.P1 = inst->d_pmat + (size_t)px * inst->pmat_stride;
         d.P2 = inst->d_pmat + (size_t)py * inst->pmat_stride;
         if (fused)
-        {  // tip operands read the edge's tip table instead of P
-          if (x.tip >= 0) d.P1 += inst->pmat_elems;
-          if (y.tip >= 0) d.P2 += inst->pmat_elems;
+        {  // tip operands read the edge's tip table instead of P, and pre-translated row indices
+          if (x.tip >= 0)
+          {
+            d.P1 += inst->pmat_elems;
+            d.t1 = inst->d_tiprows + (size_t)x.tip * inst->tip_stride;
+          }
+          if (y.tip >= 0)
+          {
+            d.P2 += inst->pmat_elems;
+            d.t2 = inst->d_tiprows + (size_t)y.tip * inst->tip_stride;
+          }
         }
         d.flags = kind;
         d.pad[0] = d.pad[1] = d.pad[2] = 0;

@@ -256,7 +256,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-constexpr int kTravStages = 4;
+constexpr int kTravStages = 8;
 constexpr int kTravComputeWarps = 7;  // + 1 producer warp = 256 threads, 2 blocks/SM at 128 registers
 constexpr int kTravThreads = (kTravComputeWarps + 1) * 32;
 
@@ -358,16 +358,14 @@ __device__ __forceinline__ void trav_operands(const TravStage<NCATG> &stg, int c
 template <int NCATG, int UMAX>
 __global__ void __launch_bounds__(kTravThreads, 2)
     k_traverse_dna(const OpDev *__restrict__ ops, int n_ops, int npat, int tile_sites, int n_tiles,
-                   const double *__restrict__ wght, const uint32_t *__restrict__ tipmask, int apply_scaling)
+                   const double *__restrict__ wght, int apply_scaling)
 {
   static_assert(NCATG == 1 || NCATG == 2 || NCATG == 4 || NCATG == 8, "NCATG must divide the warp");
-  constexpr int      S = kTravStages;
-  constexpr int      CT = kTravComputeWarps * 32;  // compute threads
+  constexpr int      S = (NCATG >= 8) ? kTravStages / 2 : kTravStages;  // static shared memory <= 48 KB
   constexpr uint32_t PB = NCATG * 16 * sizeof(double);   // P
   constexpr uint32_t TB = NCATG * 64 * sizeof(double);   // tip table
   __shared__ TravStage<NCATG>       st[S];
   __shared__ __align__(8) uint64_t full[S], empty[S];
-  __shared__ uint32_t               smask[256];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0)
@@ -378,7 +376,6 @@ __global__ void __launch_bounds__(kTravThreads, 2)
       mbar_init(&empty[s], kTravComputeWarps);
     }
   }
-  for (int i = tid; i < 256; i += kTravThreads) smask[i] = (uint32_t)tip_row4((int)tipmask[i]);  // code -> table row
   __syncthreads();
 
   const int       rounds = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -486,12 +483,12 @@ __global__ void __launch_bounds__(kTravThreads, 2)
     if (ka == kSrcTip)                                                                 \
     {                                                                                  \
       const uint8_t *tp = on.t1;                                                       \
-      _Pragma("unroll") for (int u = 0; u < UMAX; ++u) mA[u] = smask[tp[sidx[u]]];     \
+      _Pragma("unroll") for (int u = 0; u < UMAX; ++u) mA[u] = tp[sidx[u]];            \
     }                                                                                  \
     if (kb == kSrcTip)                                                                 \
     {                                                                                  \
       const uint8_t *tp = on.t2;                                                       \
-      _Pragma("unroll") for (int u = 0; u < UMAX; ++u) mB[u] = smask[tp[sidx[u]]];     \
+      _Pragma("unroll") for (int u = 0; u < UMAX; ++u) mB[u] = tp[sidx[u]];            \
     }                                                                                  \
   }
 
@@ -578,6 +575,14 @@ __global__ void __launch_bounds__(kTravThreads, 2)
     }
 #undef PLK_FETCH
   }
+}
+
+// tip codes -> rows of the 4-state tip tables (run once per tip upload; t1/t2 of fused ops point here)
+__global__ void k_codes_to_rows(const uint8_t *__restrict__ codes, uint8_t *__restrict__ rows, size_t n,
+                                const uint32_t *__restrict__ tipmask)
+{
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    rows[i] = (uint8_t)tip_row4((int)tipmask[codes[i]]);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -211,8 +211,8 @@ class Engine:
 
     # ------------------------------------------------------------------ K0
     def update_pmats(self, handles: Iterable[int], lengths: Iterable[float]):
-        h = np.ascontiguousarray(list(handles), dtype=np.int32)
-        l = np.ascontiguousarray(list(lengths), dtype=np.float64)
+        h = np.ascontiguousarray(handles if isinstance(handles, np.ndarray) else list(handles), dtype=np.int32)
+        l = np.ascontiguousarray(lengths if isinstance(lengths, np.ndarray) else list(lengths), dtype=np.float64)
         assert h.shape == l.shape
         self._ck(self.lib.plk_update_pmats(self.h, len(h), _ptr(h), _ptr(l)))
 
