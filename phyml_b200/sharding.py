@@ -1,0 +1,40 @@
+"""Site sharding across ranks: every rank owns a contiguous block of site
+patterns of every buffer; the only exchange is the sum of the per-rank partial lnL (and d lnL).
+
+Two transports for that sum:
+  * the engine's own NCCL communicator (plk_comm_init): the all-reduce is enqueued on the engine
+    stream right behind the reduction kernel -- the product path on GPUs;
+  * a torch.distributed process group (gloo on CPU, used by the world_size-2 tests of the host
+    logic; also usable with nccl) -- `dist_reduce_fn`.
+"""
+from __future__ import annotations
+
+from typing import Callable, Sequence
+
+from .alignment import Patterns, shard_bounds  # noqa: F401  (re-exported)
+
+
+def dist_reduce_fn(group=None) -> Callable[[Sequence[float]], Sequence[float]]:
+    """reduce_fn for LkTree: element-wise SUM over the ranks of a torch.distributed group."""
+    import torch
+    import torch.distributed as dist
+
+    def reduce(vals):
+        backend = dist.get_backend(group)
+        dev = "cuda" if backend == "nccl" else "cpu"
+        t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return t.tolist()
+
+    return reduce
+
+
+def init_engine_comm(engine, rank: int, world: int, group=None) -> None:
+    """Create the engine-internal NCCL communicator; the 128-byte id travels over `group`."""
+    import torch.distributed as dist
+
+    from .engine import Engine
+
+    uid = [Engine.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0, group=group)
+    engine.comm_init(rank, world, uid[0])

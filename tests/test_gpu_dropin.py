@@ -1,0 +1,77 @@
+"""Drop-in test (config 5 of BASELINE.json in miniature): the UNMODIFIED reference (its main(), spr.c,
+optimiz.c, models.c ... built from /root/reference into oracle/_ref/libphyml_ref.so) driving the B200
+engine through integration/lk_b200_shim.c, compared with the same reference running its own AVX
+likelihood.  Both binaries are build products that travel to the GPU box; skipped if absent."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+B200 = os.path.join(ROOT, "integration", "_build", "phyml_b200")
+REF = os.path.join(ROOT, "oracle", "_ref", "phyml_ref")
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+needs_bins = pytest.mark.skipif(not (os.path.exists(B200) and os.path.exists(REF)),
+                                reason="drop-in binaries not built (need /root/reference at build time)")
+
+
+def run(binary, tmp, args, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    res = subprocess.run([binary] + args, cwd=tmp, capture_output=True, text=True, timeout=900, env=e)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    m = re.findall(r"Log likelihood of the current tree: (-?[0-9]+\.[0-9]+)", res.stdout)
+    assert m, res.stdout[-2000:]
+    return float(m[-1]), res.stdout
+
+
+def stage(tmp_path, name):
+    for ext in (".phy", ".nwk"):
+        shutil.copy(os.path.join(GOLD, name + ext), tmp_path)
+    return name + ".phy", name + ".nwk"
+
+
+@needs_bins
+def test_fixed_tree_lnl_matches_reference(tmp_path):
+    """-o n: main() -> Lk(NULL) twice; value printed with 21 decimals must agree to 1e-11 relative."""
+    phy, nwk = stage(tmp_path, "synth_dna_deep")
+    args = ["-i", phy, "-u", nwk, "-d", "nt", "-m", "GTR", "-c", "4", "-a", "0.5", "-f", "e", "-o", "n", "-b", "0",
+            "--r_seed", "1", "--no_memory_check"]
+    a, _ = run(B200, str(tmp_path), args)
+    b, _ = run(REF, str(tmp_path), args)
+    assert abs(a - b) <= 1e-11 * abs(b), (a, b)
+    assert abs(b - (-21640.146617685834)) <= 1e-9 * abs(b)
+
+
+@needs_bins
+def test_branch_length_and_rate_optimisation(tmp_path):
+    """-o lr: Round_Optimize / Br_Len_Opt / dLk of optimiz.c, unchanged, on the GPU engine."""
+    phy, nwk = stage(tmp_path, "synth_dna_deep")
+    args = ["-i", phy, "-u", nwk, "-d", "nt", "-m", "HKY85", "-c", "4", "-f", "e", "-o", "lr", "-b", "0",
+            "--r_seed", "1", "--no_memory_check"]
+    a, out = run(B200, str(tmp_path), args, {"PLK_SHIM_VERBOSE": "1"})
+    b, _ = run(REF, str(tmp_path), args)
+    assert "phyml_b200: Lk" in out
+    assert abs(a - b) <= 1e-6 * abs(b), (a, b)
+
+
+@needs_bins
+def test_spr_search(tmp_path):
+    """-o tlr -s SPR: Global_Spr_Search of spr.c (Prune/Graft pointer swaps, Update_Partial_Lk per
+    candidate, Lk(b), Triple_Dist) on the GPU engine; the final lnL must match the CPU run's."""
+    phy, nwk = stage(tmp_path, "synth_dna_deep")
+    # 200 taxa is a long CPU search: use the first 24 taxa of the alignment
+    lines = open(os.path.join(str(tmp_path), phy)).read().splitlines()
+    n_sites = lines[0].split()[1]
+    with open(os.path.join(str(tmp_path), "small.phy"), "w") as f:
+        f.write(f"24 {n_sites}\n" + "\n".join(lines[1:25]) + "\n")
+    args = ["-i", "small.phy", "-d", "nt", "-m", "HKY85", "-c", "4", "-a", "0.5", "-f", "e", "-o", "tlr", "-s", "SPR",
+            "-b", "0", "--r_seed", "1", "--no_memory_check"]
+    a, out = run(B200, str(tmp_path), args, {"PLK_SHIM_VERBOSE": "1"})
+    b, _ = run(REF, str(tmp_path), args)
+    assert abs(a - b) <= 1e-5 * abs(b), (a, b)
