@@ -120,6 +120,7 @@ struct plk_instance
   double l_min = 1e-8, l_max = 100.0;  // host copy of mod->l_min / l_max (plk_set_model)
   int    trav_umax = 2;                // items per thread of the fused traversal kernel
   int    trav_blocks_per_sm = 2;
+  bool   aa_attr_set = false;
 
   // scheduling scratch
   std::vector<int> lvl_write, lvl_read, op_level;
@@ -353,7 +354,8 @@ int plk_create(const plk_config *cfg, plk_instance **out)
   const size_t P = (size_t)cfg->n_patterns;
   inst->tip_stride = (P + 127) & ~(size_t)127;
   inst->pmat_elems = (size_t)cfg->ncatg * cfg->ns * cfg->ns;
-  inst->pmat_stride = inst->pmat_elems + (cfg->ns == 4 ? (size_t)cfg->ncatg * 64 : 0);
+  inst->pmat_stride = inst->pmat_elems + (cfg->ns == 4 ? (size_t)cfg->ncatg * 64 : 0) +
+                      (cfg->ns == 20 ? (size_t)cfg->ncatg * 420 : 0);
   inst->clv.assign(cfg->n_clv, nullptr);
   inst->scale.assign(cfg->n_clv, nullptr);
 
@@ -361,7 +363,7 @@ int plk_create(const plk_config *cfg, plk_instance **out)
   CREATE_RC(dev_alloc(inst, &inst->d_invar, P));
   CREATE_RC(dev_alloc(inst, &inst->d_tipmask, 256));
   CREATE_RC(dev_alloc(inst, &inst->d_tipcodes, inst->tip_stride * cfg->n_tips));
-  if (cfg->ns == 4) CREATE_RC(dev_alloc(inst, &inst->d_tiprows, inst->tip_stride * cfg->n_tips));
+  if (cfg->ns == 4 || cfg->ns == 20) CREATE_RC(dev_alloc(inst, &inst->d_tiprows, inst->tip_stride * cfg->n_tips));
   CREATE_RC(dev_alloc(inst, &inst->d_model, 1));
   CREATE_RC(dev_alloc(inst, &inst->d_pmat, inst->pmat_stride * cfg->n_pmat));
   CREATE_RC(dev_alloc(inst, &inst->d_site_lnl, P));
@@ -584,7 +586,7 @@ int plk_update_pmats(plk_instance *inst, int n, const int *pmat, const double *l
     void *d = nullptr;
     int   rc = stage_upload(inst, jobs.data(), sizeof(PmatJob) * cnt, &d);
     if (rc) return rc;
-    k_pmat<<<cnt * nc, threads, smem, inst->stream>>>((const PmatJob *)d, inst->d_model, ns, nc, ns == 4 ? 1 : 0);
+    k_pmat<<<cnt * nc, threads, smem, inst->stream>>>((const PmatJob *)d, inst->d_model, ns, nc, ns == 4 ? 1 : (ns == 20 ? 2 : 0));
     inst->launches++;
     CU_TRY(inst, cudaGetLastError());
   }
@@ -609,6 +611,21 @@ int plk_set_pmat(plk_instance *inst, int pmat, const double *P)
           if (m & 8) a = a + row[3];
           rec[inst->pmat_elems + (size_t)c * 64 + tip_row4(m) * 4 + i] = a;
         }
+  }
+  if (inst->cfg.ns == 20)
+  {  // tPx[c][s][i] = P[c][i][s], row 20 = ascending-j row sums (same as k_pmat)
+    for (int c = 0; c < inst->cfg.ncatg; ++c)
+    {
+      const double *Pc = P + (size_t)c * 400;
+      double       *TX = rec.data() + inst->pmat_elems + (size_t)c * 420;
+      for (int i = 0; i < 20; ++i)
+      {
+        double a = Pc[i * 20];
+        for (int j = 1; j < 20; ++j) a = a + Pc[i * 20 + j];
+        TX[20 * 20 + i] = a;
+        for (int sidx = 0; sidx < 20; ++sidx) TX[sidx * 20 + i] = Pc[i * 20 + sidx];
+      }
+    }
   }
   const size_t b = inst->pmat_stride * sizeof(double);
   double      *dstp = inst->d_pmat + (size_t)pmat * inst->pmat_stride;
@@ -661,6 +678,33 @@ static int launch_traverse_t(plk_instance *inst, const OpDev *d_ops, int n_ops, 
   return PLK_OK;
 }
 
+// fused 20-state traversal on the FP64 tensor pipe
+static int launch_traverse_aa(plk_instance *inst, const OpDev *d_ops, int n_ops)
+{
+  const int    nc = inst->cfg.ncatg, P = inst->cfg.n_patterns;
+  const size_t smem = (size_t)kAaStages * aa_stage_bytes(nc);
+  if (!inst->aa_attr_set)
+  {
+    CU_TRY(inst, cudaFuncSetAttribute(k_traverse_aa, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    inst->aa_attr_set = true;
+  }
+  const int slots = inst->num_sms * 2;
+  const long long cap = (long long)slots * kAaTileCap;
+  const int       rounds = (int)((P + cap - 1) / cap);
+  int             n_tiles = std::max(1, std::min(slots * rounds, (P + 7) / 8));
+  int             tile_sites = (P + n_tiles - 1) / n_tiles;
+  tile_sites = ((tile_sites + 7) / 8) * 8;
+  if (tile_sites > kAaTileCap) tile_sites = kAaTileCap;
+  n_tiles = (P + tile_sites - 1) / tile_sites;
+  const int       grid = std::min(n_tiles, slots);
+  const long long code_delta = (long long)(inst->d_tipcodes - inst->d_tiprows);
+  k_traverse_aa<<<grid, kTravThreads, smem, inst->stream>>>(d_ops, n_ops, P, nc, tile_sites, n_tiles, inst->d_wght,
+                                                          inst->d_tipmask, code_delta, inst->apply_scaling);
+  inst->launches++;
+  CU_TRY(inst, cudaGetLastError());
+  return PLK_OK;
+}
+
 // fused traversal launch: tiles of `tile_sites` patterns, persistent blocks (2 per SM), every block
 // gets the same number of equally sized tiles so there is no tail wave
 static int launch_traverse(plk_instance *inst, const OpDev *d_ops, int n_ops)
@@ -708,12 +752,18 @@ int plk_update_partials(plk_instance *inst, int n_ops, const plk_op *ops)
   if (n_ops == 0) return PLK_OK;
   const int  nclv = inst->cfg.n_clv;
   const int  nc = inst->cfg.ncatg;
-  const bool fused = (inst->cfg.ns == 4) && (nc == 1 || nc == 2 || nc == 4 || nc == 8);
+  const bool fused_dna = (inst->cfg.ns == 4) && (nc == 1 || nc == 2 || nc == 4 || nc == 8);
+  const bool fused_aa = (inst->cfg.ns == 20) && nc <= 8 && !getenv("PLK_AA_GENERIC");
+  const bool fused = fused_dna || fused_aa;
   if (fused && inst->tiprows_dirty)
   {
     const size_t n = inst->tip_stride * inst->cfg.n_tips;
-    k_codes_to_rows<<<(unsigned)std::min<size_t>((n + 255) / 256, 4096), 256, 0, inst->stream>>>(
-        inst->d_tipcodes, inst->d_tiprows, n, inst->d_tipmask);
+    if (fused_dna)
+      k_codes_to_rows<<<(unsigned)std::min<size_t>((n + 255) / 256, 4096), 256, 0, inst->stream>>>(
+          inst->d_tipcodes, inst->d_tiprows, n, inst->d_tipmask);
+    else
+      k_codes_to_rows20<<<(unsigned)std::min<size_t>((n + 255) / 256, 4096), 256, 0, inst->stream>>>(
+          inst->d_tipcodes, inst->d_tiprows, n, inst->d_tipmask);
     inst->launches++;
     CU_TRY(inst, cudaGetLastError());
     inst->tiprows_dirty = false;
@@ -787,7 +837,7 @@ int plk_update_partials(plk_instance *inst, int n_ops, const plk_op *ops)
         plk_side x = o.c1, y = o.c2;
         int      px = o.pmat1, py = o.pmat2;
         int      kind = 0;
-        if (fused)
+        if (fused_dna)
         {
           // canonical operand order (the product of the children commutes exactly): a child that is
           // the previous update's destination first (forwarded in registers), CLVs before tips
@@ -826,6 +876,7 @@ int plk_update_partials(plk_instance *inst, int n_ops, const plk_op *ops)
             d.t2 = inst->d_tiprows + (size_t)y.tip * inst->tip_stride;
           }
         }
+        if (fused_aa) kind = (x.tip >= 0 ? 1 : 0) | (y.tip >= 0 ? 2 : 0);
         d.flags = kind;
         d.pad[0] = d.pad[1] = d.pad[2] = 0;
         host.push_back(d);
@@ -838,8 +889,9 @@ int plk_update_partials(plk_instance *inst, int n_ops, const plk_op *ops)
     if (rc) return rc;
     for (auto &lc : launches)
     {
-      rc = fused ? launch_traverse(inst, (const OpDev *)d + lc.first, lc.second)
-                 : launch_level_generic(inst, (const OpDev *)d + lc.first, lc.second);
+      rc = fused_dna ? launch_traverse(inst, (const OpDev *)d + lc.first, lc.second)
+           : fused_aa ? launch_traverse_aa(inst, (const OpDev *)d + lc.first, lc.second)
+                      : launch_level_generic(inst, (const OpDev *)d + lc.first, lc.second);
       if (rc) return rc;
     }
   }

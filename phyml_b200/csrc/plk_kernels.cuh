@@ -175,7 +175,22 @@ __global__ void k_pmat(const PmatJob *__restrict__ jobs, const ModelDev *__restr
     pn = raw[e] / sum;                                          // models.c:298
     jobs[job].P[(size_t)c * nn + e] = pn;
   }
-  if (with_tip_table)
+  if (with_tip_table == 2)
+  {  // ns == 20: tPx[c][s][i] = P[c][i][s] for s < 20 (what an unambiguous tip in state s contributes) and
+     // tPx[c][20][i] = sum_j P[c][i][j] in ascending j (a fully ambiguous tip: gap / X / ?)
+    __syncthreads();
+    if (e < nn) raw[e] = pn;
+    __syncthreads();
+    double *TX = jobs[job].P + (size_t)ncatg * nn + (size_t)c * 420;
+    if (e < nn) TX[(e % ns) * ns + (e / ns)] = pn;
+    if (e < ns)
+    {
+      double a = raw[e * ns];
+      for (int j = 1; j < ns; ++j) a = a + raw[e * ns + j];
+      TX[20 * ns + e] = a;
+    }
+  }
+  else if (with_tip_table)
   {  // ns == 4: TP[c][tip_row4(mask)][i] = sum_{j in mask} P[c][i][j], ascending j (a tip child's vector)
     __syncthreads();
     if (e < nn) raw[e] = pn;
@@ -577,12 +592,362 @@ __global__ void __launch_bounds__(kTravThreads, 2)
   }
 }
 
+// tip codes -> rows of the 20-state tip tables: state for one-hot codes, 20 for all-ones, 255 = general mask
+__global__ void k_codes_to_rows20(const uint8_t *__restrict__ codes, uint8_t *__restrict__ rows, size_t n,
+                                  const uint32_t *__restrict__ tipmask)
+{
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+  {
+    const uint32_t m = tipmask[codes[i]] & 0xFFFFFu;
+    rows[i] = (__popc(m) == 1) ? (uint8_t)(__ffs(m) - 1) : (m == 0xFFFFFu ? (uint8_t)20 : (uint8_t)255);
+  }
+}
+
 // tip codes -> rows of the 4-state tip tables (run once per tip upload; t1/t2 of fused ops point here)
 __global__ void k_codes_to_rows(const uint8_t *__restrict__ codes, uint8_t *__restrict__ rows, size_t n,
                                 const uint32_t *__restrict__ tipmask)
 {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     rows[i] = (uint8_t)tip_row4((int)tipmask[codes[i]]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 fused traversal, 20 states, on the FP64 tensor pipe (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4).
+// The per-category update  dst[s][i] = (sum_j P1[i][j] x1[s][j]) * (sum_j P2[i][j] x2[s][j])  is the
+// dense contraction (sites x 20) . (20 x 20): sites are the M dimension (8 per m-tile), output states
+// the N dimension (3 n-tiles, 20 padded to 24), input states the K dimension (5 k-steps of 4).
+//   A fragment (row = lane>>2 = site, col = lane&3): child CLV words, 5 LDG.64 per m-tile and child
+//   B fragment (k = lane&3, n = lane>>2): P[n0+n][k0+k], 15 doubles per child, held in REGISTERS for
+//     all m-tiles of the warp (loaded once per update and category from the TMA-staged copy in smem)
+//   C fragment (row = site, cols 2*(lane&3), +1): 6 doubles per child; the product of the two
+//     children's fragments is the output tile, stored as three 16-byte words per thread.
+// A warp owns kAaU m-tiles (8 sites each) and loops over the categories; a tip child needs no MMA:
+// its fragment is read from the transposed tip table tPx (row = state, or the all-ones row).
+// The per-site maximum for the 2^256 rescaling (avx.c:498-510) is tracked while the categories
+// stream through; the (rare) rescaling re-reads the thread's own stores.
+// Same warp roles / TMA-mbarrier ring as k_traverse_dna; CLVs written by an update are re-read by
+// later updates of the same warp (different lanes: __syncwarp() after every update).
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
+{
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double ldg64(const double *p)
+{
+  double v;
+  asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void stg128(double *p, double x, double y)
+{
+  asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(x), "d"(y) : "memory");
+}
+__device__ __forceinline__ void ldg128(const double *p, double &x, double &y)
+{
+  asm volatile("ld.global.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "l"(p) : "memory");
+}
+
+constexpr int kAaStages = 3;
+constexpr int kAaU = 2;  // m-tiles (of 8 sites) per warp
+constexpr int kAaTileCap = kTravComputeWarps * 8 * kAaU;
+__host__ __device__ inline size_t aa_stage_bytes(int ncatg) { return 128 + 2 * (size_t)ncatg * 420 * sizeof(double); }
+
+// C fragment of a tip child: u[i] = sum_{j in mask} P[i][j] for the thread's output states
+__device__ __forceinline__ void aa_tip_frag(const double *tpx /* [21][20] of this category */, int row, uint32_t mask,
+                                            int t, double (&cf)[6])
+{
+  if (row <= 20)
+  {
+#pragma unroll
+    for (int n = 0; n < 3; ++n)
+    {
+      const int i0 = n * 8 + 2 * t;
+      if (i0 < 20)
+      {
+        cf[2 * n] = tpx[row * 20 + i0];
+        cf[2 * n + 1] = tpx[row * 20 + i0 + 1];
+      }
+      else
+        cf[2 * n] = cf[2 * n + 1] = 0.0;
+    }
+  }
+  else
+  {  // general ambiguity code: ascending-j sum of the selected columns (same order as the reference)
+#pragma unroll
+    for (int n = 0; n < 3; ++n)
+    {
+      const int i0 = n * 8 + 2 * t;
+      double    a0 = 0.0, a1 = 0.0;
+      bool      first = true;
+      if (i0 < 20)
+        for (int j = 0; j < 20; ++j)
+          if ((mask >> j) & 1u)
+          {
+            a0 = first ? tpx[j * 20 + i0] : a0 + tpx[j * 20 + i0];
+            a1 = first ? tpx[j * 20 + i0 + 1] : a1 + tpx[j * 20 + i0 + 1];
+            first = false;
+          }
+      cf[2 * n] = a0;
+      cf[2 * n + 1] = a1;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kTravThreads, 2)
+    k_traverse_aa(const OpDev *__restrict__ ops, int n_ops, int npat, int ncatg, int tile_sites, int n_tiles,
+                  const double *__restrict__ wght, const uint32_t *__restrict__ tipmask, long long code_delta,
+                  int apply_scaling)
+{
+  constexpr int                      S = kAaStages;
+  extern __shared__ __align__(128) unsigned char aa_smem[];
+  __shared__ __align__(8) uint64_t   full[S], empty[S];
+  const size_t   stage_bytes = aa_stage_bytes(ncatg);
+  const uint32_t PB = (uint32_t)(ncatg * 400 * sizeof(double));
+  const uint32_t TB = (uint32_t)(ncatg * 420 * sizeof(double));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0)
+    for (int s = 0; s < S; ++s)
+    {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kTravComputeWarps);
+    }
+  __syncthreads();
+
+  const int       rounds = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const long long total_it = (long long)rounds * n_ops;
+
+  if (warp == kTravComputeWarps)
+  {  // ---------------- producer warp
+    for (long long base = 0; base < total_it; base += 32)
+    {
+      const long long    my = base + lane;
+      unsigned long long m1 = 0, m2 = 0;
+      int                kd = 0;
+      if (my < total_it)
+      {
+        const OpDev *o = ops + (my % n_ops);
+        m1 = (unsigned long long)o->P1;
+        m2 = (unsigned long long)o->P2;
+        kd = o->flags;
+      }
+      const int cnt = (int)min((long long)32, total_it - base);
+      for (int j = 0; j < cnt; ++j)
+      {
+        const unsigned long long a1 = __shfl_sync(0xffffffffu, m1, j), a2 = __shfl_sync(0xffffffffu, m2, j);
+        const int                kind = __shfl_sync(0xffffffffu, kd, j);
+        if (lane == 0)
+        {
+          const long long it = base + j;
+          const int       s = (int)(it % S);
+          const uint32_t  ph = (uint32_t)((it / S) & 1);
+          unsigned char  *stg = aa_smem + (size_t)s * stage_bytes;
+          mbar_wait(&empty[s], ph ^ 1u);
+          const uint32_t b1 = (kind & 1) ? TB : PB;
+          const uint32_t b2 = (kind & 2) ? TB : PB;
+          mbar_expect_tx(&full[s], (uint32_t)sizeof(OpDev) + b1 + b2);
+          tma_bulk_g2s(stg, ops + (it % n_ops), (uint32_t)sizeof(OpDev), &full[s]);
+          tma_bulk_g2s(stg + 128, (const void *)a1, b1, &full[s]);
+          tma_bulk_g2s(stg + 128 + (size_t)ncatg * 420 * sizeof(double), (const void *)a2, b2, &full[s]);
+        }
+        __syncwarp();
+      }
+    }
+    return;
+  }
+
+  // ---------------- compute warps
+  const int    g = lane >> 2, t = lane & 3;
+  const int    ncns = ncatg * 20;
+  const double big = two_to_large(), small = inv_two_to_large();
+  long long    it = 0;
+  for (int r = 0; r < rounds; ++r)
+  {
+    const int tile = (int)blockIdx.x + r * (int)gridDim.x;
+    const int base_site = tile * tile_sites;
+    const int n_sites = min(tile_sites, npat - base_site);
+    int       site[kAaU];
+    bool      valid[kAaU], live[kAaU];
+#pragma unroll
+    for (int u = 0; u < kAaU; ++u)
+    {
+      const int ls = (u * kTravComputeWarps + warp) * 8 + g;
+      valid[u] = ls < n_sites;
+      site[u] = base_site + (valid[u] ? ls : n_sites - 1);
+      live[u] = valid[u] && (wght[site[u]] > DBL_MIN);
+    }
+
+    for (int k = 0; k < n_ops; ++k, ++it)
+    {
+      const int            s = (int)(it % S);
+      const uint32_t       ph = (uint32_t)((it / S) & 1);
+      const unsigned char *stg = aa_smem + (size_t)s * stage_bytes;
+      mbar_wait(&full[s], ph);
+      const OpDev  &op = *reinterpret_cast<const OpDev *>(stg);
+      const double *M1 = reinterpret_cast<const double *>(stg + 128);
+      const double *M2 = M1 + (size_t)ncatg * 420;
+      const double *c1 = op.c1, *c2 = op.c2;
+      const bool    tip1 = (c1 == nullptr), tip2 = (c2 == nullptr);
+      double *const dst = op.dst;
+
+      int      sc[kAaU], row1[kAaU], row2[kAaU];
+      uint32_t msk1[kAaU], msk2[kAaU];
+      double   mx[kAaU];
+#pragma unroll
+      for (int u = 0; u < kAaU; ++u)
+      {
+        sc[u] = 0;
+        mx[u] = -DBL_MAX;
+        row1[u] = row2[u] = 0;
+        msk1[u] = msk2[u] = 0u;
+        if (tip1)
+        {
+          row1[u] = op.t1[site[u]];
+          if (row1[u] > 20) msk1[u] = tipmask[(op.t1 + code_delta)[site[u]]] & 0xFFFFFu;
+        }
+        else
+          sc[u] += op.s1[site[u]];
+        if (tip2)
+        {
+          row2[u] = op.t2[site[u]];
+          if (row2[u] > 20) msk2[u] = tipmask[(op.t2 + code_delta)[site[u]]] & 0xFFFFFu;
+        }
+        else
+          sc[u] += op.s2[site[u]];
+      }
+
+      for (int c = 0; c < ncatg; ++c)
+      {
+        double cf1[kAaU][6], cf2[kAaU][6];
+        bool   one1[kAaU], one2[kAaU];
+        // ---- child 1
+        if (!tip1)
+        {
+          double bf[15];
+          const double *P = M1 + (size_t)c * 400;
+#pragma unroll
+          for (int n = 0; n < 3; ++n)
+#pragma unroll
+            for (int kk = 0; kk < 5; ++kk)
+              bf[n * 5 + kk] = (n * 8 + g < 20) ? P[(n * 8 + g) * 20 + kk * 4 + t] : 0.0;
+#pragma unroll
+          for (int u = 0; u < kAaU; ++u)
+          {
+            const double *row = c1 + (size_t)site[u] * ncns + c * 20 + t;
+            double        a[5];
+#pragma unroll
+            for (int kk = 0; kk < 5; ++kk) a[kk] = ldg64(row + kk * 4);
+            const bool mine = (a[0] == 1.0) && (a[1] == 1.0) && (a[2] == 1.0) && (a[3] == 1.0) && (a[4] == 1.0);
+            const unsigned bal = __ballot_sync(0xffffffffu, mine);
+            one1[u] = ((bal >> (lane & ~3)) & 0xFu) == 0xFu;
+#pragma unroll
+            for (int n = 0; n < 3; ++n)
+            {
+              cf1[u][2 * n] = cf1[u][2 * n + 1] = 0.0;
+#pragma unroll
+              for (int kk = 0; kk < 5; ++kk) dmma884(cf1[u][2 * n], cf1[u][2 * n + 1], a[kk], bf[n * 5 + kk]);
+            }
+          }
+        }
+        else
+        {
+#pragma unroll
+          for (int u = 0; u < kAaU; ++u)
+          {
+            aa_tip_frag(M1 + (size_t)c * 420, row1[u], msk1[u], t, cf1[u]);
+            one1[u] = (row1[u] == 20);
+          }
+        }
+        // ---- child 2
+        if (!tip2)
+        {
+          double bf[15];
+          const double *P = M2 + (size_t)c * 400;
+#pragma unroll
+          for (int n = 0; n < 3; ++n)
+#pragma unroll
+            for (int kk = 0; kk < 5; ++kk)
+              bf[n * 5 + kk] = (n * 8 + g < 20) ? P[(n * 8 + g) * 20 + kk * 4 + t] : 0.0;
+#pragma unroll
+          for (int u = 0; u < kAaU; ++u)
+          {
+            const double *row = c2 + (size_t)site[u] * ncns + c * 20 + t;
+            double        a[5];
+#pragma unroll
+            for (int kk = 0; kk < 5; ++kk) a[kk] = ldg64(row + kk * 4);
+            const bool mine = (a[0] == 1.0) && (a[1] == 1.0) && (a[2] == 1.0) && (a[3] == 1.0) && (a[4] == 1.0);
+            const unsigned bal = __ballot_sync(0xffffffffu, mine);
+            one2[u] = ((bal >> (lane & ~3)) & 0xFu) == 0xFu;
+#pragma unroll
+            for (int n = 0; n < 3; ++n)
+            {
+              cf2[u][2 * n] = cf2[u][2 * n + 1] = 0.0;
+#pragma unroll
+              for (int kk = 0; kk < 5; ++kk) dmma884(cf2[u][2 * n], cf2[u][2 * n + 1], a[kk], bf[n * 5 + kk]);
+            }
+          }
+        }
+        else
+        {
+#pragma unroll
+          for (int u = 0; u < kAaU; ++u)
+          {
+            aa_tip_frag(M2 + (size_t)c * 420, row2[u], msk2[u], t, cf2[u]);
+            one2[u] = (row2[u] == 20);
+          }
+        }
+        // ---- product, running maximum, store
+#pragma unroll
+        for (int u = 0; u < kAaU; ++u)
+        {
+          double      *out = dst + (size_t)site[u] * ncns + c * 20 + 2 * t;
+          const bool   ones = one1[u] && one2[u];  // avx.c:575-587
+#pragma unroll
+          for (int n = 0; n < 3; ++n)
+          {
+            if (n * 8 + 2 * t < 20)
+            {
+              const double o0 = ones ? 1.0 : cf1[u][2 * n] * cf2[u][2 * n];
+              const double o1 = ones ? 1.0 : cf1[u][2 * n + 1] * cf2[u][2 * n + 1];
+              mx[u] = fmax(mx[u], fmax(o0, o1));
+              if (live[u]) stg128(out + n * 8, o0, o1);
+            }
+          }
+        }
+      }
+
+      // ---- per-site maximum over all categories and states, rescaling (avx.c:498-510)
+#pragma unroll
+      for (int u = 0; u < kAaU; ++u)
+      {
+        double m = mx[u];
+        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 1));
+        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 2));
+        int sco = sc[u];
+        if (m < small && apply_scaling)
+        {
+          sco += kLarge;
+          if (live[u])
+            for (int c = 0; c < ncatg; ++c)
+            {
+              double *out = dst + (size_t)site[u] * ncns + c * 20 + 2 * t;
+#pragma unroll
+              for (int n = 0; n < 3; ++n)
+                if (n * 8 + 2 * t < 20)
+                {
+                  double x, y;
+                  ldg128(out + n * 8, x, y);
+                  stg128(out + n * 8, x * big, y * big);
+                }
+            }
+        }
+        if (live[u] && t == 0) op.dst_scale[site[u]] = sco;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
