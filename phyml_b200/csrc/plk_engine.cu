@@ -93,6 +93,7 @@ struct plk_instance
   double *d_dot_prod = nullptr;
   double *d_partials = nullptr;
   int    *d_warn = nullptr;
+  unsigned int *d_ticket = nullptr;
   double *d_result = nullptr;
 
   ResultHost        *h_result = nullptr;
@@ -233,15 +234,24 @@ int reduce_grid(const plk_instance *inst, int threads)
   return std::max(1, std::min(need, std::min(kMaxReduceBlocks, inst->num_sms * 16)));
 }
 
-// finish a reduction: second stage, optional all-reduce, publish, wait
-int finish_reduction(plk_instance *inst, int nblocks, int nv, double *out0, double *out1, int *warn)
+// where the reduction kernel about to be launched delivers its result
+ReduceOut make_reduce_out(plk_instance *inst)
 {
-  const unsigned long long seq = ++inst->seq;
-  const int                publish = inst->allreduce ? 0 : 1;
-  k_reduce_final<<<1, 256, 0, inst->stream>>>(inst->d_partials, nblocks, nv, inst->d_result, inst->d_warn,
-                                              inst->h_result_dev, seq, publish);
-  inst->launches++;
-  CU_TRY(inst, cudaGetLastError());
+  ReduceOut ro;
+  ro.partials = inst->d_partials;
+  ro.ticket = inst->d_ticket;
+  ro.warn_flag = inst->d_warn;
+  ro.dev_out = inst->d_result;
+  ro.host_out = inst->h_result_dev;
+  ro.seq = ++inst->seq;
+  ro.publish = inst->allreduce ? 0 : 1;
+  return ro;
+}
+
+// finish a reduction: optional all-reduce + publish, then wait for the mapped result
+int finish_reduction(plk_instance *inst, double *out0, double *out1, int *warn)
+{
+  const unsigned long long seq = inst->seq;
   if (inst->allreduce)
   {
     // the warning flag travels as a third double so that one sum all-reduce carries everything
@@ -372,6 +382,7 @@ int plk_create(const plk_config *cfg, plk_instance **out)
   CREATE_RC(dev_alloc(inst, &inst->d_fact, P));
   CREATE_RC(dev_alloc(inst, &inst->d_partials, (size_t)kMaxReduceBlocks * 2));
   CREATE_RC(dev_alloc(inst, &inst->d_warn, 1));
+  CREATE_RC(dev_alloc(inst, &inst->d_ticket, 1));
   CREATE_RC(dev_alloc(inst, &inst->d_result, 4));
   CREATE_RC(dev_alloc(inst, &inst->d_stage, (size_t)kStageSlots * kStageBytes));
   CREATE_TRY(cudaMemsetAsync(inst->d_wght, 0, P * sizeof(double), inst->stream));
@@ -379,6 +390,7 @@ int plk_create(const plk_config *cfg, plk_instance **out)
   CREATE_TRY(cudaMemsetAsync(inst->d_tipmask, 0, 256 * sizeof(uint32_t), inst->stream));
   CREATE_TRY(cudaMemsetAsync(inst->d_tipcodes, 0, inst->tip_stride * cfg->n_tips, inst->stream));
   CREATE_TRY(cudaMemsetAsync(inst->d_warn, 0, sizeof(int), inst->stream));
+  CREATE_TRY(cudaMemsetAsync(inst->d_ticket, 0, sizeof(unsigned int), inst->stream));
   CREATE_TRY(cudaMemsetAsync(inst->d_pmat, 0, inst->pmat_stride * cfg->n_pmat * sizeof(double), inst->stream));
   CREATE_TRY(cudaMemsetAsync(inst->d_fact, 0, P * sizeof(int), inst->stream));
 
@@ -419,6 +431,7 @@ void plk_destroy(plk_instance *inst)
   cudaFree(inst->d_dot_prod);
   cudaFree(inst->d_partials);
   cudaFree(inst->d_warn);
+  cudaFree(inst->d_ticket);
   cudaFree(inst->d_result);
   cudaFree(inst->d_stage);
   if (inst->h_result) cudaFreeHost(inst->h_result);
@@ -911,11 +924,11 @@ int plk_edge_lnl(plk_instance *inst, plk_side left, plk_side rght, int pmat, dou
                                              inst->d_pmat + (size_t)pmat * inst->pmat_stride, inst->d_model,
                                              inst->cfg.n_patterns, inst->cfg.ns, inst->cfg.ncatg, inst->d_wght,
                                              inst->d_invar, inst->d_tipmask, inst->d_site_lnl, inst->d_site_lk,
-                                             inst->d_site_lk_cat, inst->d_fact, inst->d_partials, inst->d_warn);
+                                             inst->d_site_lk_cat, inst->d_fact, make_reduce_out(inst));
   inst->launches++;
   CU_TRY(inst, cudaGetLastError());
   inst->site_valid = true;
-  return finish_reduction(inst, grid, 1, lnl, nullptr, warn);
+  return finish_reduction(inst, lnl, nullptr, warn);
 }
 
 // ---- K3 ------------------------------------------------------------------------------------------
@@ -953,10 +966,10 @@ static int run_k4(plk_instance *inst, double l, int deriv, double *lnl, double *
   const int grid = reduce_grid(inst, 128);
   k_lnl_dlnl<<<grid, 128, 0, inst->stream>>>(inst->d_dot_prod, inst->d_fact, inst->d_model, l, deriv,
                                              inst->cfg.n_patterns, inst->cfg.ns, inst->cfg.ncatg, inst->d_wght,
-                                             inst->d_invar, inst->d_site_lnl, inst->d_partials, inst->d_warn);
+                                             inst->d_invar, inst->d_site_lnl, make_reduce_out(inst));
   inst->launches++;
   CU_TRY(inst, cudaGetLastError());
-  return finish_reduction(inst, grid, 2, lnl, dlnl, warn);
+  return finish_reduction(inst, lnl, dlnl, warn);
 }
 
 int plk_edge_lnl_dlnl(plk_instance *inst, double *l, double *lnl, double *dlnl, int *warn)

@@ -7,7 +7,7 @@
 // K2  k_edge_lnl        edge log-likelihood + per-site by-products        (lk.c:605-645, 767-861, 2777-2801)
 // K3  k_eigen_lr        eigen-basis projection dot_prod                   (lk.c:1038-1114, avx.c:21-105)
 // K4  k_lnl_dlnl        lnL and dlnL/dl from dot_prod                     (lk.c:655-753, 955-1032)
-//     k_reduce_final    deterministic second stage of the lnL reductions
+//     (K2/K4 end with a deterministic last-block reduction that publishes to mapped pinned memory)
 //
 // Arithmetic order: where it is free, sums are accumulated in the order of the reference's AVX+FMA
 // kernels (first term a plain product, then an FMA chain in ascending state order; horizontal sums
@@ -119,6 +119,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
       "}" ::"r"(smem_u32(bar)),
       "r"(parity)
       : "memory");
+}
+// producer-side wait: backs off between probes so the spinning lane does not eat issue slots
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity)
+{
+  uint32_t done = 0;
+  while (true)
+  {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(64);
+  }
 }
 __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
 {
@@ -422,7 +441,7 @@ __global__ void __launch_bounds__(kTravThreads, 2)
           const long long it = base + j;
           const int       s = (int)(it % S);
           const uint32_t  ph = (uint32_t)((it / S) & 1);
-          mbar_wait(&empty[s], ph ^ 1u);
+          mbar_wait_backoff(&empty[s], ph ^ 1u);
           const uint32_t b1 = ((kind & 3) == kSrcTip) ? TB : PB;
           const uint32_t b2 = ((kind >> 2) == kSrcTip) ? TB : PB;
           mbar_expect_tx(&full[s], (uint32_t)sizeof(OpDev) + b1 + b2);
@@ -517,6 +536,62 @@ __global__ void __launch_bounds__(kTravThreads, 2)
       PLK_FETCH(s0)
     }
 
+    // one update, fully specialised on its operand kinds: operands -> prefetch of the next update's
+    // operands -> products / per-site max / rescaling / store.  Nothing is merged across kinds, so no
+    // register shuffling between the specialisations.
+#define PLK_UPDATE(KA, KB)                                                                                    \
+  {                                                                                                           \
+    double uA[UMAX][4], uB[UMAX][4];                                                                          \
+    bool   ones[UMAX];                                                                                        \
+    int    sc[UMAX];                                                                                          \
+    trav_operands<NCATG, UMAX, KA, KB>(stg, cat, off4, sidx, prev_o, prev_sc, slot_v, slot_sc, mA, mB, uA, uB, \
+                                       ones, sc);                                                             \
+    if (k + 1 < n_ops)                                                                                        \
+    {                                                                                                         \
+      const int      sn = (int)((it + 1) % S);                                                                \
+      const uint32_t phn = (uint32_t)(((it + 1) / S) & 1);                                                    \
+      mbar_wait(&full[sn], phn);                                                                              \
+      PLK_FETCH(sn)                                                                                           \
+    }                                                                                                         \
+    _Pragma("unroll") for (int u = 0; u < UMAX; ++u)                                                          \
+    {                                                                                                         \
+      double4a o;                                                                                             \
+      if (ones[u])                                                                                            \
+      {                                                                                                       \
+        o.x = o.y = o.z = o.w = 1.0;                                                                          \
+      }                                                                                                       \
+      else                                                                                                    \
+      {                                                                                                       \
+        o.x = uA[u][0] * uB[u][0];                                                                            \
+        o.y = uA[u][1] * uB[u][1];                                                                            \
+        o.z = uA[u][2] * uB[u][2];                                                                            \
+        o.w = uA[u][3] * uB[u][3];                                                                            \
+      }                                                                                                       \
+      /* avx.c:498-510: is the largest entry of the site below 2^-256?  All entries are >= 0, so the   */     \
+      /* test is an integer compare of the exponent words (NaN counts as large, like the reference).   */     \
+      const unsigned hi = (unsigned)max(max(__double2hiint(o.x), __double2hiint(o.y)),                        \
+                                        max(__double2hiint(o.z), __double2hiint(o.w)));                       \
+      unsigned       hmax = hi;                                                                               \
+      _Pragma("unroll") for (int d = SW; d < 32; d <<= 1) hmax = max(hmax, __shfl_xor_sync(0xffffffffu, hmax, d)); \
+      int sco = sc[u];                                                                                        \
+      if (hmax < 0x2FF00000u && apply_scaling)                                                                \
+      {                                                                                                       \
+        o.x *= big;                                                                                           \
+        o.y *= big;                                                                                           \
+        o.z *= big;                                                                                           \
+        o.w *= big;                                                                                           \
+        sco += kLarge;                                                                                        \
+      }                                                                                                       \
+      if (live[u])                                                                                            \
+      {                                                                                                       \
+        stg256(dst + off4[u], o);                                                                             \
+        if (cat == 0) dst_scale[sidx[u]] = sco;                                                               \
+      }                                                                                                       \
+      prev_o[u] = o;                                                                                          \
+      prev_sc[u] = sco;                                                                                       \
+    }                                                                                                         \
+  }
+
     for (int k = 0; k < n_ops; ++k, ++it)
     {
       const int                s = (int)(it % S);
@@ -524,70 +599,18 @@ __global__ void __launch_bounds__(kTravThreads, 2)
       const int                kind = nx_kind;
       double *const            dst = nx_dst;
       int *const               dst_scale = nx_dst_scale;
-
-      double uA[UMAX][4], uB[UMAX][4];
-      bool   ones[UMAX];
-      int    sc[UMAX];
-#define PLK_OPERANDS(KA, KB) \
-  trav_operands<NCATG, UMAX, KA, KB>(stg, cat, off4, sidx, prev_o, prev_sc, slot_v, slot_sc, mA, mB, uA, uB, ones, sc)
       switch (kind)
       {
-      case (kSrcFwd | (kSrcTip << 2)): PLK_OPERANDS(kSrcFwd, kSrcTip); break;
-      case (kSrcFwd | (kSrcSlot << 2)): PLK_OPERANDS(kSrcFwd, kSrcSlot); break;
-      case (kSrcTip | (kSrcTip << 2)): PLK_OPERANDS(kSrcTip, kSrcTip); break;
-      case (kSrcSlot | (kSrcTip << 2)): PLK_OPERANDS(kSrcSlot, kSrcTip); break;
-      default: PLK_OPERANDS(kSrcSlot, kSrcLate); break;
-      }
-#undef PLK_OPERANDS
-
-      // the operands of this update are consumed: prefetch those of the next one
-      if (k + 1 < n_ops)
-      {
-        const int      sn = (int)((it + 1) % S);
-        const uint32_t phn = (uint32_t)(((it + 1) / S) & 1);
-        mbar_wait(&full[sn], phn);
-        PLK_FETCH(sn)
-      }
-
-#pragma unroll
-      for (int u = 0; u < UMAX; ++u)
-      {
-        double4a o;
-        if (ones[u])
-        {  // avx.c:575-587
-          o.x = o.y = o.z = o.w = 1.0;
-        }
-        else
-        {
-          o.x = uA[u][0] * uB[u][0];
-          o.y = uA[u][1] * uB[u][1];
-          o.z = uA[u][2] * uB[u][2];
-          o.w = uA[u][3] * uB[u][3];
-        }
-        // avx.c:498-510
-        double mx = fmax(fmax(o.x, o.y), fmax(o.z, o.w));
-#pragma unroll
-        for (int d = SW; d < 32; d <<= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-        int sco = sc[u];
-        if (mx < small && apply_scaling)
-        {
-          o.x *= big;
-          o.y *= big;
-          o.z *= big;
-          o.w *= big;
-          sco += kLarge;
-        }
-        if (live[u])
-        {
-          stg256(dst + off4[u], o);
-          if (cat == 0) dst_scale[sidx[u]] = sco;
-        }
-        prev_o[u] = o;
-        prev_sc[u] = sco;
+      case (kSrcFwd | (kSrcTip << 2)): PLK_UPDATE(kSrcFwd, kSrcTip) break;
+      case (kSrcFwd | (kSrcSlot << 2)): PLK_UPDATE(kSrcFwd, kSrcSlot) break;
+      case (kSrcTip | (kSrcTip << 2)): PLK_UPDATE(kSrcTip, kSrcTip) break;
+      case (kSrcSlot | (kSrcTip << 2)): PLK_UPDATE(kSrcSlot, kSrcTip) break;
+      default: PLK_UPDATE(kSrcSlot, kSrcLate) break;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
     }
+#undef PLK_UPDATE
 #undef PLK_FETCH
   }
 }
@@ -743,7 +766,7 @@ __global__ void __launch_bounds__(kTravThreads, 2)
           const int       s = (int)(it % S);
           const uint32_t  ph = (uint32_t)((it / S) & 1);
           unsigned char  *stg = aa_smem + (size_t)s * stage_bytes;
-          mbar_wait(&empty[s], ph ^ 1u);
+          mbar_wait_backoff(&empty[s], ph ^ 1u);
           const uint32_t b1 = (kind & 1) ? TB : PB;
           const uint32_t b2 = (kind & 2) ? TB : PB;
           mbar_expect_tx(&full[s], (uint32_t)sizeof(OpDev) + b1 + b2);
@@ -1018,12 +1041,37 @@ __global__ void __launch_bounds__(128)
 }
 
 // ------------------------------------------------------------------------------------------------
-// Block reduction of up to 2 running sums, deterministic: fixed shuffle tree, fixed warp order.
+// result block shared with the host through mapped pinned memory
+struct ResultHost
+{
+  double            val[2];
+  int               warn;
+  int               pad;
+  unsigned long long seq;
+};
+
+// where a reduction kernel delivers its result
+struct ReduceOut
+{
+  double              *partials;  // [gridDim.x][NV]
+  unsigned int        *ticket;    // last-block detection
+  int                 *warn_flag;
+  double              *dev_out;   // [3]: values, warning as double (for the all-reduce)
+  volatile ResultHost *host_out;
+  unsigned long long   seq;
+  int                  publish;   // 1: write host_out here; 0: an all-reduce + k_publish follow
+};
+
+// Deterministic reduction of up to 2 running sums in ONE launch: fixed shuffle tree per warp, fixed
+// warp order per block, per-block partials to global memory; the block that finishes last (atomic
+// ticket) adds the partials in index order and publishes the result.  The order of the additions
+// does not depend on which block happens to be last.
 template <int NV>
-__device__ __forceinline__ void block_reduce_store(double (&v)[NV], int warn, double *partials, int *warn_out)
+__device__ __forceinline__ void block_reduce_finish(double (&v)[NV], int warn, const ReduceOut &ro)
 {
   __shared__ double sred[NV][32];
   __shared__ int    swarn;
+  __shared__ bool   is_last;
   if (threadIdx.x == 0) swarn = 0;
   __syncthreads();
 #pragma unroll
@@ -1042,55 +1090,45 @@ __device__ __forceinline__ void block_reduce_store(double (&v)[NV], int warn, do
 #pragma unroll
     for (int k = 0; k < NV; ++k)
     {
-      double s = 0.0;
-      for (int w = 0; w < nw; ++w) s += sred[k][w];
-      partials[(size_t)blockIdx.x * NV + k] = s;
+      double sacc = 0.0;
+      for (int w = 0; w < nw; ++w) sacc += sred[k][w];
+      ro.partials[(size_t)blockIdx.x * NV + k] = sacc;
     }
-    if (swarn) atomicOr(warn_out, 1);
+    if (swarn) atomicOr(ro.warn_flag, 1);
+    __threadfence();
+    const unsigned int t = atomicAdd(ro.ticket, 1u);
+    is_last = (t == gridDim.x - 1);
   }
-}
-
-// result block shared with the host through mapped pinned memory
-struct ResultHost
-{
-  double            val[2];
-  int               warn;
-  int               pad;
-  unsigned long long seq;
-};
-
-// second stage: sums the per-block partials in index order, publishes to the host
-__global__ void k_reduce_final(const double *__restrict__ partials, int nblocks, int nv, double *dev_out,
-                               int *warn_flag, volatile ResultHost *host_out, unsigned long long seq, int publish)
-{
-  __shared__ double s[2][256];
-  for (int k = 0; k < nv; ++k)
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // last block: every thread adds a strided subset in index order, thread 0 adds the per-thread sums
+  __shared__ double sfin[NV][128];
+  for (int k = 0; k < NV; ++k)
   {
     double a = 0.0;
-    for (int b = threadIdx.x; b < nblocks; b += 256) a += partials[(size_t)b * nv + k];
-    s[k][threadIdx.x] = a;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) a += ro.partials[(size_t)b * NV + k];
+    sfin[k][threadIdx.x] = a;
   }
   __syncthreads();
   if (threadIdx.x == 0)
   {
     double r[2] = {0.0, 0.0};
-    for (int k = 0; k < nv; ++k)
-      for (int t = 0; t < 256; ++t) r[k] += s[k][t];
-    dev_out[0] = r[0];
-    dev_out[1] = r[1];
-    const int w = *warn_flag;
-    *warn_flag = 0;
-    if (publish)
+    for (int k = 0; k < NV; ++k)
+      for (int t = 0; t < (int)blockDim.x; ++t) r[k] += sfin[k][t];
+    const int w = *ro.warn_flag;
+    *ro.warn_flag = 0;
+    *ro.ticket = 0u;
+    ro.dev_out[0] = r[0];
+    ro.dev_out[1] = r[1];
+    ro.dev_out[2] = (double)w;
+    if (ro.publish)
     {
-      host_out->val[0] = r[0];
-      host_out->val[1] = r[1];
-      host_out->warn = w;
+      ro.host_out->val[0] = r[0];
+      ro.host_out->val[1] = r[1];
+      ro.host_out->warn = w;
       __threadfence_system();
-      host_out->seq = seq;
-    }
-    else
-    {
-      dev_out[2] = (double)w;  // summed across ranks with the values: > 0 means some rank warned
+      ro.host_out->seq = ro.seq;
     }
   }
 }
@@ -1134,7 +1172,7 @@ __global__ void __launch_bounds__(128)
     k_edge_lnl(SideDev left, SideDev rght, const double *__restrict__ P, const ModelDev *__restrict__ mod, int npat,
                int ns, int ncatg, const double *__restrict__ wght, const short *__restrict__ invar,
                const uint32_t *__restrict__ tipmask, double *__restrict__ site_lnl, double *__restrict__ site_lk_out,
-               double *__restrict__ site_lk_cat, int *__restrict__ fact_sum_scale, double *partials, int *warn_out)
+               double *__restrict__ site_lk_cat, int *__restrict__ fact_sum_scale, ReduceOut ro)
 {
   const int    ncns = ncatg * ns, nn = ns * ns;
   const double *pi = mod->pi;
@@ -1244,7 +1282,7 @@ __global__ void __launch_bounds__(128)
     fact_sum_scale[site] = fact;
     acc[0] += w * lsl;  // lk.c:856
   }
-  block_reduce_store<1>(acc, warn, partials, warn_out);
+  block_reduce_finish<1>(acc, warn, ro);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1293,7 +1331,7 @@ __global__ void __launch_bounds__(128)
     k_lnl_dlnl(const double *__restrict__ dot_prod, const int *__restrict__ fact_sum_scale,
                const ModelDev *__restrict__ mod, double l, int with_derivative, int npat, int ns, int ncatg,
                const double *__restrict__ wght, const short *__restrict__ invar, double *__restrict__ site_lnl,
-               double *partials, int *warn_out)
+               ReduceOut ro)
 {
   __shared__ double sE[kMaxCatg * kMaxNs], sD[kMaxCatg * kMaxNs];
   const int         ncns = ncatg * ns;
@@ -1408,7 +1446,7 @@ __global__ void __launch_bounds__(128)
     acc[0] += w * lsl;
     acc[1] += w * (dlk / lk);
   }
-  block_reduce_store<2>(acc, warn, partials, warn_out);
+  block_reduce_finish<2>(acc, warn, ro);
 }
 
 }  // namespace plk
