@@ -37,12 +37,10 @@ def test_full_traversal_exact(case):
     """K1 reproduces the reference's AVX+FMA arithmetic order: with the reference's P-matrices every
     CLV (post- and pre-order) and every scaler must be BIT-IDENTICAL to the reference's."""
     c, eng = make(case)
-    if c.ns == 4:
-        pc.check_full_traversal(c, eng, clv_rtol=0, exact=True)
-    else:
-        # 20 states run on the FP64 tensor pipe (DMMA): the accumulation order inside the MMA is not the
-        # reference's FMA chain, so CLVs agree to a few ulps per update instead of bit for bit
-        pc.check_full_traversal(c, eng, clv_rtol=2e-13, exact=False)
+    # 20 states run on the FP64 tensor pipe: on B200 DMMA.8x8x4 accumulates as an ascending-k FMA chain
+    # (tools/probes/dmma_order.cu: 262144/262144 products identical), i.e. exactly the reference's
+    # AVX_Matrix_Vect_Prod order, so the tensor-core path is bit-identical too
+    pc.check_full_traversal(c, eng, clv_rtol=0, exact=True)
 
 
 @pytest.mark.parametrize("case", ALL_CASES)
