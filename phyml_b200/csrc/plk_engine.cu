@@ -122,6 +122,8 @@ struct plk_instance
   int    trav_umax = 2;                // items per thread of the fused traversal kernel
   int    trav_blocks_per_sm = 2;
   bool   aa_attr_set = false;
+  int    blocked = 0;            // CLVs in the blocked layout (ns = 4, 20), see clv_off()
+  double *d_tmp_clv = nullptr;   // plain-layout staging for plk_get_clv / plk_set_clv
 
   // scheduling scratch
   std::vector<int> lvl_write, lvl_read, op_level;
@@ -159,9 +161,15 @@ int dev_alloc(plk_instance *inst, T **p, size_t n)
   return PLK_OK;
 }
 
-size_t clv_elems(const plk_instance *inst)
+// elements of one CLV in the caller's (plain) layout / in device memory (blocked layout pads to 8 sites)
+size_t clv_elems_plain(const plk_instance *inst)
 {
   return (size_t)inst->cfg.n_patterns * inst->cfg.ncatg * inst->cfg.ns;
+}
+size_t clv_elems(const plk_instance *inst)
+{
+  const size_t sites = inst->blocked ? (((size_t)inst->cfg.n_patterns + 7) & ~(size_t)7) : (size_t)inst->cfg.n_patterns;
+  return sites * inst->cfg.ncatg * inst->cfg.ns;
 }
 
 int ensure_clv(plk_instance *inst, int h)
@@ -331,6 +339,12 @@ int plk_create(const plk_config *cfg, plk_instance **out)
   plk_instance *inst = new plk_instance();
   inst->cfg = *cfg;
   inst->apply_scaling = (cfg->flags & PLK_FLAG_NO_SCALING) ? 0 : 1;
+  {  // the blocked layout goes with the fused kernels; the generic kernel keeps the reference's layout
+    const int  nc = cfg->ncatg;
+    const bool fdna = (cfg->ns == 4) && (nc == 1 || nc == 2 || nc == 4 || nc == 8);
+    const bool faa = (cfg->ns == 20) && nc <= 8 && !getenv("PLK_AA_GENERIC");
+    inst->blocked = (fdna || faa) ? 1 : 0;
+  }
   auto fail = [&](int rc) {
     g_create_error = inst->err;
     plk_destroy(inst);
@@ -429,6 +443,7 @@ void plk_destroy(plk_instance *inst)
   cudaFree(inst->d_site_lk_cat);
   cudaFree(inst->d_fact);
   cudaFree(inst->d_dot_prod);
+  cudaFree(inst->d_tmp_clv);
   cudaFree(inst->d_partials);
   cudaFree(inst->d_warn);
   cudaFree(inst->d_ticket);
@@ -734,6 +749,7 @@ static int launch_traverse(plk_instance *inst, const OpDev *d_ops, int n_ops)
   const int min_tile = std::max(1, CT / nc);
   n_tiles = std::max(1, std::min(n_tiles, (P + min_tile - 1) / min_tile));
   int tile_sites = (P + n_tiles - 1) / n_tiles;
+  tile_sites = std::min(((tile_sites + 7) / 8) * 8, std::max(8, (CT * umax / nc) / 8 * 8));  // whole 8-site blocks
   n_tiles = (P + tile_sites - 1) / tile_sites;
   const int grid = std::min(n_tiles, slots);
   if ((long long)tile_sites * nc > (long long)CT * umax)
@@ -924,7 +940,7 @@ int plk_edge_lnl(plk_instance *inst, plk_side left, plk_side rght, int pmat, dou
                                              inst->d_pmat + (size_t)pmat * inst->pmat_stride, inst->d_model,
                                              inst->cfg.n_patterns, inst->cfg.ns, inst->cfg.ncatg, inst->d_wght,
                                              inst->d_invar, inst->d_tipmask, inst->d_site_lnl, inst->d_site_lk,
-                                             inst->d_site_lk_cat, inst->d_fact, make_reduce_out(inst));
+                                             inst->d_site_lk_cat, inst->d_fact, make_reduce_out(inst), inst->blocked);
   inst->launches++;
   CU_TRY(inst, cudaGetLastError());
   inst->site_valid = true;
@@ -940,15 +956,15 @@ int plk_eigen_lr(plk_instance *inst, plk_side left, plk_side rght)
   if (rc) return rc;
   if (!inst->d_dot_prod)
   {
-    rc = dev_alloc(inst, &inst->d_dot_prod, clv_elems(inst));
+    rc = dev_alloc(inst, &inst->d_dot_prod, clv_elems_plain(inst));
     if (rc) return rc;
-    CU_TRY(inst, cudaMemsetAsync(inst->d_dot_prod, 0, clv_elems(inst) * sizeof(double), inst->stream));
+    CU_TRY(inst, cudaMemsetAsync(inst->d_dot_prod, 0, clv_elems_plain(inst) * sizeof(double), inst->stream));
   }
   const long long work = (long long)inst->cfg.n_patterns * inst->cfg.ncatg;
   const int       grid = (int)std::max<long long>(1, std::min<long long>((work + 127) / 128, inst->num_sms * 32));
   k_eigen_lr<<<grid, 128, 0, inst->stream>>>(side_dev(inst, left), side_dev(inst, rght), inst->d_model,
                                              inst->cfg.n_patterns, inst->cfg.ns, inst->cfg.ncatg, inst->d_wght,
-                                             inst->d_tipmask, inst->d_dot_prod, inst->d_fact);
+                                             inst->d_tipmask, inst->d_dot_prod, inst->d_fact, inst->blocked);
   inst->launches++;
   CU_TRY(inst, cudaGetLastError());
   inst->eigen_ready = true;
@@ -992,13 +1008,32 @@ int plk_edge_lnl_eigen(plk_instance *inst, double l, double *lnl, int *warn)
 }
 
 // ---- read-backs ------------------------------------------------------------------------------------
+static int ensure_tmp_clv(plk_instance *inst)
+{
+  if (inst->d_tmp_clv) return PLK_OK;
+  return dev_alloc(inst, &inst->d_tmp_clv, clv_elems_plain(inst));
+}
+
 int plk_get_clv(plk_instance *inst, int h, double *clv_out, int *scale_out)
 {
   ARG_CHECK(inst, h >= 0 && h < inst->cfg.n_clv, "clv handle out of range");
   ARG_CHECK(inst, inst->clv[h] != nullptr, "clv handle was never written");
   if (clv_out)
-    CU_TRY(inst, cudaMemcpyAsync(clv_out, inst->clv[h], clv_elems(inst) * sizeof(double), cudaMemcpyDeviceToHost,
+  {
+    const double *src = inst->clv[h];
+    if (inst->blocked)
+    {  // device-side conversion to the reference's [site][catg][state] layout
+      int rc = ensure_tmp_clv(inst);
+      if (rc) return rc;
+      k_clv_convert<<<inst->num_sms * 4, 256, 0, inst->stream>>>(inst->clv[h], inst->d_tmp_clv, inst->cfg.n_patterns,
+                                                                   inst->cfg.ncatg, inst->cfg.ns, 0);
+      inst->launches++;
+      CU_TRY(inst, cudaGetLastError());
+      src = inst->d_tmp_clv;
+    }
+    CU_TRY(inst, cudaMemcpyAsync(clv_out, src, clv_elems_plain(inst) * sizeof(double), cudaMemcpyDeviceToHost,
                                  inst->stream));
+  }
   if (scale_out)
     CU_TRY(inst, cudaMemcpyAsync(scale_out, inst->scale[h], (size_t)inst->cfg.n_patterns * sizeof(int),
                                  cudaMemcpyDeviceToHost, inst->stream));
@@ -1011,8 +1046,20 @@ int plk_set_clv(plk_instance *inst, int h, const double *clv_in, const int *scal
   ARG_CHECK(inst, h >= 0 && h < inst->cfg.n_clv && clv_in, "clv handle out of range");
   int rc = ensure_clv(inst, h);
   if (rc) return rc;
-  CU_TRY(inst, cudaMemcpyAsync(inst->clv[h], clv_in, clv_elems(inst) * sizeof(double), cudaMemcpyHostToDevice,
-                               inst->stream));
+  if (inst->blocked)
+  {
+    rc = ensure_tmp_clv(inst);
+    if (rc) return rc;
+    CU_TRY(inst, cudaMemcpyAsync(inst->d_tmp_clv, clv_in, clv_elems_plain(inst) * sizeof(double), cudaMemcpyHostToDevice,
+                                 inst->stream));
+    k_clv_convert<<<inst->num_sms * 4, 256, 0, inst->stream>>>(inst->d_tmp_clv, inst->clv[h], inst->cfg.n_patterns,
+                                                                 inst->cfg.ncatg, inst->cfg.ns, 1);
+    inst->launches++;
+    CU_TRY(inst, cudaGetLastError());
+  }
+  else
+    CU_TRY(inst, cudaMemcpyAsync(inst->clv[h], clv_in, clv_elems_plain(inst) * sizeof(double), cudaMemcpyHostToDevice,
+                                 inst->stream));
   if (scale_in)
     CU_TRY(inst, cudaMemcpyAsync(inst->scale[h], scale_in, (size_t)inst->cfg.n_patterns * sizeof(int),
                                  cudaMemcpyHostToDevice, inst->stream));
@@ -1038,7 +1085,7 @@ int plk_get_site_lnl(plk_instance *inst, double *site_lnl, double *site_lk, doub
 int plk_get_dot_prod(plk_instance *inst, double *dot_prod)
 {
   ARG_CHECK(inst, dot_prod && inst->d_dot_prod, "dot_prod not computed yet");
-  CU_TRY(inst, cudaMemcpyAsync(dot_prod, inst->d_dot_prod, clv_elems(inst) * sizeof(double), cudaMemcpyDeviceToHost,
+  CU_TRY(inst, cudaMemcpyAsync(dot_prod, inst->d_dot_prod, clv_elems_plain(inst) * sizeof(double), cudaMemcpyDeviceToHost,
                                inst->stream));
   CU_TRY(inst, cudaStreamSynchronize(inst->stream));
   return PLK_OK;

@@ -31,6 +31,34 @@ constexpr int kLarge = 256;                        // utilities.h:507
 __device__ __forceinline__ double two_to_large() { return __longlong_as_double(0x4FF0000000000000LL); }
 __device__ __forceinline__ double inv_two_to_large() { return __longlong_as_double(0x2FF0000000000000LL); }
 
+// CLV addressing.  Plain layout (any ns): [site][catg][state], the reference's (lk.c:1474).
+// Blocked layout (ns = 4 or 20, internal to the engine; plk_get_clv/plk_set_clv convert):
+//   [tile = site/8][catg][kb = state/4][r = site%8][t = state%4]
+// so the 8 sites x 4 states that one MMA fragment load/store touches are one contiguous 256-byte block
+// and a (site, catg) item of a 4-state CLV is still one 32-byte word.
+__host__ __device__ __forceinline__ size_t clv_off(int site, int c, int i, int ncatg, int ns, int blocked)
+{
+  if (blocked)
+    return (((((size_t)(site >> 3) * ncatg + c) * (ns >> 2) + (i >> 2)) * 8 + (site & 7)) << 2) + (i & 3);
+  return ((size_t)site * ncatg + c) * ns + i;
+}
+
+// plain <-> blocked conversion of one CLV (read-back / upload paths)
+__global__ void k_clv_convert(const double *__restrict__ src, double *__restrict__ dst, int npat, int ncatg, int ns,
+                              int to_blocked)
+{
+  const size_t total = (size_t)npat * ncatg * ns;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x)
+  {
+    const int    i = (int)(e % ns), c = (int)((e / ns) % ncatg), site = (int)(e / ((size_t)ns * ncatg));
+    const size_t b = clv_off(site, c, i, ncatg, ns, 1);
+    if (to_blocked)
+      dst[b] = src[e];
+    else
+      dst[e] = src[b];
+  }
+}
+
 struct __align__(32) double4a
 {
   double x, y, z, w;
@@ -477,7 +505,7 @@ __global__ void __launch_bounds__(kTravThreads, 2)
       const int ls = (u * kTravComputeWarps + warp) * SW + (lane % SW);  // site within the tile
       const int lc = ls < n_sites ? ls : n_sites - 1;
       sidx[u] = base_site + lc;
-      off4[u] = ((long long)sidx[u] * NCATG + cat) * 4;
+      off4[u] = ((((long long)(sidx[u] >> 3) * NCATG + cat) << 3) + (sidx[u] & 7)) * 4;  // blocked layout
       live[u] = (ls < n_sites) && (wght[sidx[u]] > DBL_MIN);  // avx.c:399
     }
     (void)n_items;
@@ -782,7 +810,6 @@ __global__ void __launch_bounds__(kTravThreads, 2)
 
   // ---------------- compute warps
   const int    g = lane >> 2, t = lane & 3;
-  const int    ncns = ncatg * 20;
   const double big = two_to_large(), small = inv_two_to_large();
   long long    it = 0;
   for (int r = 0; r < rounds; ++r)
@@ -857,10 +884,10 @@ __global__ void __launch_bounds__(kTravThreads, 2)
 #pragma unroll
           for (int u = 0; u < kAaU; ++u)
           {
-            const double *row = c1 + (size_t)site[u] * ncns + c * 20 + t;
+            const double *row = c1 + (((size_t)(site[u] >> 3) * ncatg + c) * 5) * 32 + (site[u] & 7) * 4 + t;
             double        a[5];
 #pragma unroll
-            for (int kk = 0; kk < 5; ++kk) a[kk] = ldg64(row + kk * 4);
+            for (int kk = 0; kk < 5; ++kk) a[kk] = ldg64(row + kk * 32);
             const bool mine = (a[0] == 1.0) && (a[1] == 1.0) && (a[2] == 1.0) && (a[3] == 1.0) && (a[4] == 1.0);
             const unsigned bal = __ballot_sync(0xffffffffu, mine);
             one1[u] = ((bal >> (lane & ~3)) & 0xFu) == 0xFu;
@@ -895,10 +922,10 @@ __global__ void __launch_bounds__(kTravThreads, 2)
 #pragma unroll
           for (int u = 0; u < kAaU; ++u)
           {
-            const double *row = c2 + (size_t)site[u] * ncns + c * 20 + t;
+            const double *row = c2 + (((size_t)(site[u] >> 3) * ncatg + c) * 5) * 32 + (site[u] & 7) * 4 + t;
             double        a[5];
 #pragma unroll
-            for (int kk = 0; kk < 5; ++kk) a[kk] = ldg64(row + kk * 4);
+            for (int kk = 0; kk < 5; ++kk) a[kk] = ldg64(row + kk * 32);
             const bool mine = (a[0] == 1.0) && (a[1] == 1.0) && (a[2] == 1.0) && (a[3] == 1.0) && (a[4] == 1.0);
             const unsigned bal = __ballot_sync(0xffffffffu, mine);
             one2[u] = ((bal >> (lane & ~3)) & 0xFu) == 0xFu;
@@ -924,7 +951,7 @@ __global__ void __launch_bounds__(kTravThreads, 2)
 #pragma unroll
         for (int u = 0; u < kAaU; ++u)
         {
-          double      *out = dst + (size_t)site[u] * ncns + c * 20 + 2 * t;
+          double      *out = dst + (((size_t)(site[u] >> 3) * ncatg + c) * 5 + (t >> 1)) * 32 + (site[u] & 7) * 4 + 2 * (t & 1);
           const bool   ones = one1[u] && one2[u];  // avx.c:575-587
 #pragma unroll
           for (int n = 0; n < 3; ++n)
@@ -934,7 +961,7 @@ __global__ void __launch_bounds__(kTravThreads, 2)
               const double o0 = ones ? 1.0 : cf1[u][2 * n] * cf2[u][2 * n];
               const double o1 = ones ? 1.0 : cf1[u][2 * n + 1] * cf2[u][2 * n + 1];
               mx[u] = fmax(mx[u], fmax(o0, o1));
-              if (live[u]) stg128(out + n * 8, o0, o1);
+              if (live[u]) stg128(out + n * 64, o0, o1);
             }
           }
         }
@@ -954,14 +981,14 @@ __global__ void __launch_bounds__(kTravThreads, 2)
           if (live[u])
             for (int c = 0; c < ncatg; ++c)
             {
-              double *out = dst + (size_t)site[u] * ncns + c * 20 + 2 * t;
+              double *out = dst + (((size_t)(site[u] >> 3) * ncatg + c) * 5 + (t >> 1)) * 32 + (site[u] & 7) * 4 + 2 * (t & 1);
 #pragma unroll
               for (int n = 0; n < 3; ++n)
                 if (n * 8 + 2 * t < 20)
                 {
                   double x, y;
-                  ldg128(out + n * 8, x, y);
-                  stg128(out + n * 8, x * big, y * big);
+                  ldg128(out + n * 64, x, y);
+                  stg128(out + n * 64, x * big, y * big);
                 }
             }
         }
@@ -1172,9 +1199,9 @@ __global__ void __launch_bounds__(128)
     k_edge_lnl(SideDev left, SideDev rght, const double *__restrict__ P, const ModelDev *__restrict__ mod, int npat,
                int ns, int ncatg, const double *__restrict__ wght, const short *__restrict__ invar,
                const uint32_t *__restrict__ tipmask, double *__restrict__ site_lnl, double *__restrict__ site_lk_out,
-               double *__restrict__ site_lk_cat, int *__restrict__ fact_sum_scale, ReduceOut ro)
+               double *__restrict__ site_lk_cat, int *__restrict__ fact_sum_scale, ReduceOut ro, int blocked)
 {
-  const int    ncns = ncatg * ns, nn = ns * ns;
+  const int    nn = ns * ns;
   const double *pi = mod->pi;
   double       acc[1] = {0.0};
   int          warn = 0;
@@ -1192,9 +1219,14 @@ __global__ void __launch_bounds__(128)
     for (int c = 0; c < ncatg; ++c)
     {
       const double *Pc = P + (size_t)c * nn;
-      const double *L = left.clv ? left.clv + (size_t)site * ncns + c * ns : nullptr;
-      const double *R = rght.clv ? rght.clv + (size_t)site * ncns + c * ns : nullptr;
-      double        lk;
+      // operand accessors: a CLV in its (plain or blocked) layout, or the 0/1 vector of a tip mask
+      auto LV = [&](int l) -> double {
+        return left.clv ? left.clv[clv_off(site, c, l, ncatg, ns, blocked)] : (double)((lm >> l) & 1u);
+      };
+      auto RV = [&](int k) -> double {
+        return rght.clv ? rght.clv[clv_off(site, c, k, ncatg, ns, blocked)] : (double)((rm >> k) & 1u);
+      };
+      double lk;
       if ((ns & 3) == 0)
       {  // order of AVX_Lk_Core_One_Class_No_Eigen_Lr (avx.c:110-215)
         if (unamb)
@@ -1202,11 +1234,7 @@ __global__ void __launch_bounds__(128)
           double q[4] = {0.0, 0.0, 0.0, 0.0};
           for (int b = 0; b < ns; b += 4)
 #pragma unroll
-            for (int t = 0; t < 4; ++t)
-            {
-              const double lv = L ? L[b + t] : (double)((lm >> (b + t)) & 1u);
-              q[t] = q[t] + Pc[st * ns + b + t] * lv;
-            }
+            for (int t = 0; t < 4; ++t) q[t] = q[t] + Pc[st * ns + b + t] * LV(b + t);
           lk = pi[st] * hsum4(q[0], q[1], q[2], q[3]);
         }
         else
@@ -1219,13 +1247,9 @@ __global__ void __launch_bounds__(128)
             for (int t = 0; t < 4; ++t)
             {
               const int    k = b + t;
-              const double rv = R ? R[k] : (double)((rm >> k) & 1u);
+              const double rv = RV(k);
               double       a = 0.0;
-              for (int l = 0; l < ns; ++l)
-              {
-                const double lv = L ? L[l] : (double)((lm >> l) & 1u);
-                a = fma(Pc[k * ns + l], lv, a);
-              }
+              for (int l = 0; l < ns; ++l) a = fma(Pc[k * ns + l], LV(l), a);
               x[t] = a * (rv * pi[k]);
             }
             lk = lk + hsum4(x[0], x[1], x[2], x[3]);
@@ -1238,17 +1262,17 @@ __global__ void __launch_bounds__(128)
         if (unamb)
         {
           double sum = 0.0;
-          for (int l = 0; l < ns; ++l) sum = sum + Pc[st * ns + l] * (L ? L[l] : (double)((lm >> l) & 1u));
+          for (int l = 0; l < ns; ++l) sum = sum + Pc[st * ns + l] * LV(l);
           lk = sum * pi[st];
         }
         else
           for (int k = 0; k < ns; ++k)
           {
-            const double rv = R ? R[k] : (double)((rm >> k) & 1u);
+            const double rv = RV(k);
             if (rv > 0.0)
             {
               double sum = 0.0;
-              for (int l = 0; l < ns; ++l) sum = sum + Pc[k * ns + l] * (L ? L[l] : (double)((lm >> l) & 1u));
+              for (int l = 0; l < ns; ++l) sum = sum + Pc[k * ns + l] * LV(l);
               lk = lk + sum * pi[k] * rv;
             }
           }
@@ -1290,7 +1314,7 @@ __global__ void __launch_bounds__(128)
 __global__ void __launch_bounds__(128)
     k_eigen_lr(SideDev left, SideDev rght, const ModelDev *__restrict__ mod, int npat, int ns, int ncatg,
                const double *__restrict__ wght, const uint32_t *__restrict__ tipmask, double *__restrict__ dot_prod,
-               int *__restrict__ fact_sum_scale)
+               int *__restrict__ fact_sum_scale, int blocked)
 {
   const int       ncns = ncatg * ns;
   const long long total = (long long)npat * ncatg;
@@ -1299,26 +1323,23 @@ __global__ void __launch_bounds__(128)
     const int site = (int)(g / ncatg), c = (int)(g % ncatg);
     if (c == 0) fact_sum_scale[site] = (left.scale ? left.scale[site] : 0) + (rght.scale ? rght.scale[site] : 0);
     if (!(wght[site] > DBL_MIN)) continue;  // lk.c:1082
-    const double  *L = left.clv ? left.clv + (size_t)site * ncns + c * ns : nullptr;
-    const double  *R = rght.clv ? rght.clv + (size_t)site * ncns + c * ns : nullptr;
-    const uint32_t lm = L ? 0u : tipmask[left.tip[site]];
-    const uint32_t rm = R ? 0u : tipmask[rght.tip[site]];
-    double        *o = dot_prod + (size_t)site * ncns + c * ns;
+    const uint32_t lm = left.clv ? 0u : tipmask[left.tip[site]];
+    const uint32_t rm = rght.clv ? 0u : tipmask[rght.tip[site]];
+    auto           LV = [&](int j) -> double {
+      return left.clv ? left.clv[clv_off(site, c, j, ncatg, ns, blocked)] : (double)((lm >> j) & 1u);
+    };
+    auto RV = [&](int j) -> double {
+      return rght.clv ? rght.clv[clv_off(site, c, j, ncatg, ns, blocked)] : (double)((rm >> j) & 1u);
+    };
+    double *o = dot_prod + (size_t)site * ncns + c * ns;
     for (int i = 0; i < ns; ++i)
     {  // avx.c:79-84: left_i = sum_j U[j][i] (L_j pi_j), rght_i = sum_j V[i][j] R_j, first term a product
-      double a, b;
-      {
-        const double l0 = (L ? L[0] : (double)(lm & 1u)) * mod->pi[0];
-        const double r0 = R ? R[0] : (double)(rm & 1u);
-        a = mod->U[i] * l0;
-        b = mod->V[i * ns] * r0;
-      }
+      double a = mod->U[i] * (LV(0) * mod->pi[0]);
+      double b = mod->V[i * ns] * RV(0);
       for (int j = 1; j < ns; ++j)
       {
-        const double lj = (L ? L[j] : (double)((lm >> j) & 1u)) * mod->pi[j];
-        const double rj = R ? R[j] : (double)((rm >> j) & 1u);
-        a = fma(mod->U[j * ns + i], lj, a);
-        b = fma(mod->V[i * ns + j], rj, b);
+        a = fma(mod->U[j * ns + i], LV(j) * mod->pi[j], a);
+        b = fma(mod->V[i * ns + j], RV(j), b);
       }
       o[i] = a * b;
     }
