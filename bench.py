@@ -328,10 +328,12 @@ def run_reference(args):
     tree = Tree.random(n_taxa, seed=1)
     m = pmodel.gtr(alpha=0.5) if ns == 4 else pmodel.lg_from_fixture(alpha=0.5)
     cores = os.cpu_count() or 1
-    # bounded sample: a prefix of the workload's columns split over all host cores, sized so that
-    # warmup+steps evaluations end within a few minutes (1 core does ~1.7e7 updates/s)
-    per_core = max(500, min(sites // cores, int(2.0e7 * 60 / max(1, (args.steps + args.warmup)) / (n_taxa - 2))))
-    per_core = min(per_core, 12_500)
+    # bounded sample: every host core gets its own block of columns of the workload's shape (sites are
+    # independent, the reference is single-threaded: one process per core); 3 000 columns per core keeps a
+    # process's likelihood arena near 115 MB and warmup+steps evaluations within a minute or two
+    per_core = 3000 if ns == 4 else 600
+    budget = int(1.5e7 * 90 / max(1, (args.steps + args.warmup)) / (n_taxa - 2))   # ~90 s at 1.5e7 updates/s/core
+    per_core = max(200, min(per_core, budget))
     codes = alignment.simulate(tree, m, per_core * cores, seed=1000)
     cb = cpu_baseline(tree, codes, m, cores=cores, sites=per_core * cores, evals=args.steps, warm=args.warmup)
     out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,

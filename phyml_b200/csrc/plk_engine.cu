@@ -123,6 +123,8 @@ struct plk_instance
   int    trav_blocks_per_sm = 2;
   bool   aa_attr_set = false;
   int    blocked = 0;            // CLVs in the blocked layout (ns = 4, 20), see clv_off()
+  int    dna_mma = 0;            // use k_traverse_dna_mma (tensor-pipe variant) for ns = 4
+  int    mma_u = 2;
   double *d_tmp_clv = nullptr;   // plain-layout staging for plk_get_clv / plk_set_clv
 
   // scheduling scratch
@@ -372,6 +374,7 @@ int plk_create(const plk_config *cfg, plk_instance **out)
   CREATE_TRY(cudaGetDeviceProperties(&prop, cfg->device));
   inst->num_sms = prop.multiProcessorCount;
   if (const char *e = getenv("PLK_TRAV_UMAX")) inst->trav_umax = (atoi(e) == 1) ? 1 : 2;
+  if (const char *e = getenv("PLK_DNA_MMA")) inst->dna_mma = atoi(e) != 0;
   if (const char *e = getenv("PLK_TRAV_BLOCKS_PER_SM")) inst->trav_blocks_per_sm = std::max(1, std::min(4, atoi(e)));
   CREATE_TRY(cudaStreamCreateWithFlags(&inst->stream, cudaStreamNonBlocking));
 
@@ -733,6 +736,44 @@ static int launch_traverse_aa(plk_instance *inst, const OpDev *d_ops, int n_ops)
   return PLK_OK;
 }
 
+template <int NCATG, int U>
+static int launch_traverse_mma_t(plk_instance *inst, const OpDev *d_ops, int n_ops, int tile_sites, int n_tiles, int grid)
+{
+  k_traverse_dna_mma<NCATG, U><<<grid, kTravThreads, 0, inst->stream>>>(d_ops, n_ops, inst->cfg.n_patterns, tile_sites,
+                                                                        n_tiles, inst->d_wght, inst->apply_scaling);
+  inst->launches++;
+  CU_TRY(inst, cudaGetLastError());
+  return PLK_OK;
+}
+
+// tensor-pipe variant of the 4-state traversal: a block tile is 7 warps x U m-groups x 8 sites
+static int launch_traverse_mma(plk_instance *inst, const OpDev *d_ops, int n_ops)
+{
+  const int nc = inst->cfg.ncatg, P = inst->cfg.n_patterns;
+  const int U = inst->mma_u;
+  const int cap_sites = kTravComputeWarps * U * 8;
+  const int slots = inst->num_sms * inst->trav_blocks_per_sm;
+  const long long cap = (long long)slots * cap_sites;
+  const int       rounds = (int)((P + cap - 1) / cap);
+  int             n_tiles = std::max(1, std::min(slots * rounds, (P + 7) / 8));
+  int             tile_sites = (P + n_tiles - 1) / n_tiles;
+  tile_sites = std::min(((tile_sites + 7) / 8) * 8, cap_sites);
+  n_tiles = (P + tile_sites - 1) / tile_sites;
+  const int grid = std::min(n_tiles, slots);
+#define MMA_CASE(NC)                                                                                   \
+  case NC:                                                                                             \
+    return launch_traverse_mma_t<NC, 2>(inst, d_ops, n_ops, tile_sites, n_tiles, grid);
+  switch (nc)
+  {
+    MMA_CASE(1)
+    MMA_CASE(2)
+    MMA_CASE(4)
+  }
+#undef MMA_CASE
+  inst->err = "internal: unsupported ncatg for the tensor-pipe traversal kernel";
+  return PLK_ERR_ARG;
+}
+
 // fused traversal launch: tiles of `tile_sites` patterns, persistent blocks (2 per SM), every block
 // gets the same number of equally sized tiles so there is no tail wave
 static int launch_traverse(plk_instance *inst, const OpDev *d_ops, int n_ops)
@@ -918,7 +959,8 @@ int plk_update_partials(plk_instance *inst, int n_ops, const plk_op *ops)
     if (rc) return rc;
     for (auto &lc : launches)
     {
-      rc = fused_dna ? launch_traverse(inst, (const OpDev *)d + lc.first, lc.second)
+      rc = (fused_dna && inst->dna_mma && nc <= 4) ? launch_traverse_mma(inst, (const OpDev *)d + lc.first, lc.second)
+           : fused_dna ? launch_traverse(inst, (const OpDev *)d + lc.first, lc.second)
            : fused_aa ? launch_traverse_aa(inst, (const OpDev *)d + lc.first, lc.second)
                       : launch_level_generic(inst, (const OpDev *)d + lc.first, lc.second);
       if (rc) return rc;

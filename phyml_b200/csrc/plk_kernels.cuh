@@ -663,26 +663,24 @@ __global__ void k_codes_to_rows(const uint8_t *__restrict__ codes, uint8_t *__re
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1 fused traversal, 20 states, on the FP64 tensor pipe (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4).
-// The per-category update  dst[s][i] = (sum_j P1[i][j] x1[s][j]) * (sum_j P2[i][j] x2[s][j])  is the
-// dense contraction (sites x 20) . (20 x 20): sites are the M dimension (8 per m-tile), output states
-// the N dimension (3 n-tiles, 20 padded to 24), input states the K dimension (5 k-steps of 4).
-//   A fragment (row = lane>>2 = site, col = lane&3): child CLV words, 5 LDG.64 per m-tile and child
-//   B fragment (k = lane&3, n = lane>>2): P[n0+n][k0+k], 15 doubles per child, held in REGISTERS for
-//     all m-tiles of the warp (loaded once per update and category from the TMA-staged copy in smem)
-//   C fragment (row = site, cols 2*(lane&3), +1): 6 doubles per child; the product of the two
-//     children's fragments is the output tile, stored as three 16-byte words per thread.
-// A warp owns kAaU m-tiles (8 sites each) and loops over the categories; a tip child needs no MMA:
-// its fragment is read from the transposed tip table tPx (row = state, or the all-ones row).
-// The per-site maximum for the 2^256 rescaling (avx.c:498-510) is tracked while the categories
-// stream through; the (rare) rescaling re-reads the thread's own stores.
-// Same warp roles / TMA-mbarrier ring as k_traverse_dna; CLVs written by an update are re-read by
-// later updates of the same warp (different lanes: __syncwarp() after every update).
+// K1 fused traversal, 4 states, tensor-pipe variant.  With 4 states the matrix-vector product of one
+// child for 8 sites of one category is exactly ONE DMMA.8x8x4:  D[site][i] = sum_j x[site][j] P[i][j]
+// (A = 8 sites x 4 states of the child CLV, B[k=j][n=i] = P[i][j], columns 4..7 zero).  On B200 the
+// DMMA accumulates as an ascending-k FMA chain from C (tools/probes/dmma_order.cu), i.e. with C = 0 it
+// rounds exactly like the reference's AVX_Matrix_Vect_Prod, so this variant is bit-identical to
+// k_traverse_dna.  What it buys: P costs one register pair per (child, category) instead of 32
+// registers, a CLV word is ONE double per thread, so a warp carries U*8 sites x all categories
+// (4x the sites of the FMA kernel at the same register budget) and issues ~half the instructions.
+// Blocked CLV layout: every fragment load (LDG.64 x 32 lanes) / store (STG.128 x 16 lanes) is one
+// contiguous 256-byte block.  The previous update's result is forwarded in registers: its C fragment
+// (lane t<2 holds states 2t,2t+1) is turned into the next A fragment (lane t holds state t) with two
+// quad shuffles per category.
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
 {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(d0), "+d"(d1)
-               : "d"(a), "d"(b));
+  // not volatile: independent accumulator chains may be interleaved by the scheduler
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(d0), "+d"(d1)
+      : "d"(a), "d"(b));
 }
 __device__ __forceinline__ double ldg64(const double *p)
 {
@@ -699,6 +697,278 @@ __device__ __forceinline__ void ldg128(const double *p, double &x, double &y)
   asm volatile("ld.global.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "l"(p) : "memory");
 }
 
+template <int NCATG, int U>
+__global__ void __launch_bounds__(kTravThreads, 2)
+    k_traverse_dna_mma(const OpDev *__restrict__ ops, int n_ops, int npat, int tile_sites, int n_tiles,
+                       const double *__restrict__ wght, int apply_scaling)
+{
+  constexpr int      S = (NCATG >= 8) ? kTravStages / 2 : kTravStages;
+  constexpr uint32_t PB = NCATG * 16 * sizeof(double);
+  constexpr uint32_t TB = NCATG * 64 * sizeof(double);
+  __shared__ TravStage<NCATG>       st[S];
+  __shared__ __align__(8) uint64_t full[S], empty[S];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0)
+    for (int s = 0; s < S; ++s)
+    {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kTravComputeWarps);
+    }
+  __syncthreads();
+  const int       rounds = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const long long total_it = (long long)rounds * n_ops;
+
+  if (warp == kTravComputeWarps)
+  {  // ---------------- producer warp (same protocol as k_traverse_dna)
+    for (long long base = 0; base < total_it; base += 32)
+    {
+      const long long    my = base + lane;
+      unsigned long long m1 = 0, m2 = 0;
+      int                kd = 0;
+      if (my < total_it)
+      {
+        const OpDev *o = ops + (my % n_ops);
+        m1 = (unsigned long long)o->P1;
+        m2 = (unsigned long long)o->P2;
+        kd = o->flags;
+      }
+      const int cnt = (int)min((long long)32, total_it - base);
+      for (int j = 0; j < cnt; ++j)
+      {
+        const unsigned long long a1 = __shfl_sync(0xffffffffu, m1, j), a2 = __shfl_sync(0xffffffffu, m2, j);
+        const int                kind = __shfl_sync(0xffffffffu, kd, j);
+        if (lane == 0)
+        {
+          const long long it = base + j;
+          const int       s = (int)(it % S);
+          const uint32_t  ph = (uint32_t)((it / S) & 1);
+          mbar_wait_backoff(&empty[s], ph ^ 1u);
+          const uint32_t b1 = ((kind & 3) == kSrcTip) ? TB : PB;
+          const uint32_t b2 = ((kind >> 2) == kSrcTip) ? TB : PB;
+          mbar_expect_tx(&full[s], (uint32_t)sizeof(OpDev) + b1 + b2);
+          tma_bulk_g2s(&st[s].op, ops + (it % n_ops), (uint32_t)sizeof(OpDev), &full[s]);
+          tma_bulk_g2s(st[s].M[0], (const void *)a1, b1, &full[s]);
+          tma_bulk_g2s(st[s].M[1], (const void *)a2, b2, &full[s]);
+        }
+        __syncwarp();
+      }
+    }
+    return;
+  }
+
+  // ---------------- compute warps: lane = (g = site within the 8-site block, t = state / column pair)
+  const int      g = lane >> 2, t = lane & 3;
+  const int      fwd_src = (lane & ~3) | (t >> 1);  // lane holding state t in the C-fragment layout
+  const unsigned qshift = lane & ~3;
+  const double   big = two_to_large();
+  long long      it = 0;
+  for (int r = 0; r < rounds; ++r)
+  {
+    const int tile = (int)blockIdx.x + r * (int)gridDim.x;
+    const int base_site = tile * tile_sites;
+    const int n_sites = min(tile_sites, npat - base_site);
+    int       sidx[U];
+    long long boff[U];  // element offset of (8-site block, category 0)
+    bool      live[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      const int ls = (u * kTravComputeWarps + warp) * 8 + g;
+      const int lc = ls < n_sites ? ls : n_sites - 1;
+      sidx[u] = base_site + lc;
+      boff[u] = (long long)(sidx[u] >> 3) * NCATG * 32 + (sidx[u] & 7) * 4;
+      live[u] = (ls < n_sites) && (wght[sidx[u]] > DBL_MIN);
+    }
+    double   prevA[U][NCATG], slotA[U][NCATG];
+    int      prev_sc[U], slot_sc[U];
+    uint32_t rA[U], rB[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+#pragma unroll
+      for (int c = 0; c < NCATG; ++c) prevA[u][c] = slotA[u][c] = 0.0;
+      prev_sc[u] = slot_sc[u] = 0;
+      rA[u] = rB[u] = 0u;
+    }
+
+    // operand prefetch of the update staged in `sn`, for m-group u
+#define MMA_FETCH(sn, u)                                                                  \
+  {                                                                                       \
+    const OpDev &on = st[sn].op;                                                          \
+    const int    kn = on.flags, ka = kn & 3, kb = kn >> 2;                                \
+    if (ka == kSrcSlot || kb == kSrcSlot)                                                 \
+    {                                                                                     \
+      const double *lp = ((ka == kSrcSlot) ? on.c1 : on.c2) + boff[u] + t;                \
+      const int    *ls = (ka == kSrcSlot) ? on.s1 : on.s2;                                \
+      _Pragma("unroll") for (int c = 0; c < NCATG; ++c) slotA[u][c] = ldg64(lp + c * 32); \
+      slot_sc[u] = ls[sidx[u]];                                                           \
+    }                                                                                     \
+    if (ka == kSrcTip) rA[u] = on.t1[sidx[u]];                                            \
+    if (kb == kSrcTip) rB[u] = on.t2[sidx[u]];                                            \
+  }
+
+    {
+      const int      s0 = (int)(it % S);
+      const uint32_t ph0 = (uint32_t)((it / S) & 1);
+      mbar_wait(&full[s0], ph0);
+#pragma unroll
+      for (int u = 0; u < U; ++u) MMA_FETCH(s0, u)
+    }
+
+    for (int k = 0; k < n_ops; ++k, ++it)
+    {
+      const int                s = (int)(it % S);
+      const TravStage<NCATG> &stg = st[s];
+      const int                kind = stg.op.flags, ka = kind & 3, kb = kind >> 2;
+      double *const            dst = stg.op.dst;
+      int *const               dst_scale = stg.op.dst_scale;
+      const bool               has_next = (k + 1 < n_ops);
+      const int                sn = (int)((it + 1) % S);
+      if (has_next) mbar_wait(&full[sn], (uint32_t)(((it + 1) / S) & 1));
+
+      // B fragments: B[k = t][n = g] = P[c][i = g][j = t], columns 4..7 zero
+      double bA[NCATG], bB[NCATG];
+#pragma unroll
+      for (int c = 0; c < NCATG; ++c)
+      {
+        bA[c] = (ka != kSrcTip && g < 4) ? stg.M[0][c * 16 + g * 4 + t] : 0.0;
+        bB[c] = (kb != kSrcTip && g < 4) ? stg.M[1][c * 16 + g * 4 + t] : 0.0;
+      }
+
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+      {
+        double   o0[NCATG], o1[NCATG];
+        unsigned notone = 0u;  // bit c: some child value of (site, c) held by this lane differs from 1.0
+        int      sc = 0;
+        // ---- child A
+        if (ka == kSrcTip)
+        {
+          if (rA[u] != (uint32_t)kTipRowAllOnes) notone = (1u << NCATG) - 1u;
+        }
+        else
+          sc += (ka == kSrcFwd) ? prev_sc[u] : slot_sc[u];
+        double lateB[NCATG];
+        if (kb == kSrcLate)
+        {
+          const double *lp = stg.op.c2 + boff[u] + t;
+#pragma unroll
+          for (int c = 0; c < NCATG; ++c) lateB[c] = ldg64(lp + c * 32);
+          sc += stg.op.s2[sidx[u]];
+        }
+        else if (kb == kSrcSlot)
+          sc += slot_sc[u];
+        else if (rB[u] != (uint32_t)kTipRowAllOnes)
+          notone = (1u << NCATG) - 1u;
+
+#pragma unroll
+        for (int c = 0; c < NCATG; ++c)
+        {
+          double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+          if (ka == kSrcTip)
+          {
+            if (t < 2)
+            {
+              const double *tp = stg.M[0] + (c * 16 + (int)rA[u]) * 4 + 2 * t;
+              a0 = tp[0];
+              a1 = tp[1];
+            }
+          }
+          else
+          {
+            const double x = (ka == kSrcFwd) ? prevA[u][c] : slotA[u][c];
+            notone |= (((unsigned)__double2hiint(x) ^ 0x3FF00000u) | (unsigned)__double2loint(x)) ? (1u << c) : 0u;
+            dmma884(a0, a1, x, bA[c]);
+          }
+          if (kb == kSrcTip)
+          {
+            if (t < 2)
+            {
+              const double *tp = stg.M[1] + (c * 16 + (int)rB[u]) * 4 + 2 * t;
+              b0 = tp[0];
+              b1 = tp[1];
+            }
+          }
+          else
+          {
+            const double x = (kb == kSrcSlot) ? slotA[u][c] : lateB[c];
+            notone |= (((unsigned)__double2hiint(x) ^ 0x3FF00000u) | (unsigned)__double2loint(x)) ? (1u << c) : 0u;
+            dmma884(b0, b1, x, bB[c]);
+          }
+          o0[c] = a0 * b0;
+          o1[c] = a1 * b1;
+        }
+        // the operands of this m-group are consumed: prefetch those of the next update
+        if (has_next) MMA_FETCH(sn, u)
+
+        // all-ones short cut (avx.c:575-587): quad-wide OR of the "differs from 1.0" bits
+        notone |= __shfl_xor_sync(0xffffffffu, notone, 1);
+        notone |= __shfl_xor_sync(0xffffffffu, notone, 2);
+        if (notone != (1u << NCATG) - 1u)
+        {
+#pragma unroll
+          for (int c = 0; c < NCATG; ++c)
+            if (!((notone >> c) & 1u)) o0[c] = o1[c] = 1.0;
+        }
+        // avx.c:498-510: per-site maximum over all categories and states, as an exponent compare
+        int hmax = 0;
+#pragma unroll
+        for (int c = 0; c < NCATG; ++c) hmax = max(hmax, max(__double2hiint(o0[c]), __double2hiint(o1[c])));
+        const unsigned bal = __ballot_sync(0xffffffffu, (t < 2) && ((unsigned)hmax >= 0x2FF00000u));
+        if ((((bal >> qshift) & 0xFu) == 0u) && apply_scaling)
+        {
+#pragma unroll
+          for (int c = 0; c < NCATG; ++c)
+          {
+            o0[c] *= big;
+            o1[c] *= big;
+          }
+          sc += kLarge;
+        }
+        if (live[u])
+        {
+          if (t < 2)
+          {
+            double *op_ = dst + boff[u] + 2 * t;
+#pragma unroll
+            for (int c = 0; c < NCATG; ++c) stg128(op_ + c * 32, o0[c], o1[c]);
+          }
+          if (t == 0) dst_scale[sidx[u]] = sc;
+        }
+        // forward: C-fragment layout -> A-fragment layout of the next update
+#pragma unroll
+        for (int c = 0; c < NCATG; ++c)
+        {
+          const double x0 = __shfl_sync(0xffffffffu, o0[c], fwd_src);
+          const double x1 = __shfl_sync(0xffffffffu, o1[c], fwd_src);
+          prevA[u][c] = (t & 1) ? x1 : x0;
+        }
+        prev_sc[u] = sc;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+#undef MMA_FETCH
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 fused traversal, 20 states, on the FP64 tensor pipe (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4).
+// The per-category update  dst[s][i] = (sum_j P1[i][j] x1[s][j]) * (sum_j P2[i][j] x2[s][j])  is the
+// dense contraction (sites x 20) . (20 x 20): sites are the M dimension (8 per m-tile), output states
+// the N dimension (3 n-tiles, 20 padded to 24), input states the K dimension (5 k-steps of 4).
+//   A fragment (row = lane>>2 = site, col = lane&3): child CLV words, 5 LDG.64 per m-tile and child
+//   B fragment (k = lane&3, n = lane>>2): P[n0+n][k0+k], 15 doubles per child, held in REGISTERS for
+//     all m-tiles of the warp (loaded once per update and category from the TMA-staged copy in smem)
+//   C fragment (row = site, cols 2*(lane&3), +1): 6 doubles per child; the product of the two
+//     children's fragments is the output tile, stored as three 16-byte words per thread.
+// A warp owns kAaU m-tiles (8 sites each) and loops over the categories; a tip child needs no MMA:
+// its fragment is read from the transposed tip table tPx (row = state, or the all-ones row).
+// The per-site maximum for the 2^256 rescaling (avx.c:498-510) is tracked while the categories
+// stream through; the (rare) rescaling re-reads the thread's own stores.
+// Same warp roles / TMA-mbarrier ring as k_traverse_dna; CLVs written by an update are re-read by
+// later updates of the same warp (different lanes: __syncwarp() after every update).
 constexpr int kAaStages = 3;
 constexpr int kAaU = 2;  // m-tiles (of 8 sites) per warp
 constexpr int kAaTileCap = kTravComputeWarps * 8 * kAaU;
@@ -892,12 +1162,12 @@ __global__ void __launch_bounds__(kTravThreads, 2)
             const unsigned bal = __ballot_sync(0xffffffffu, mine);
             one1[u] = ((bal >> (lane & ~3)) & 0xFu) == 0xFu;
 #pragma unroll
-            for (int n = 0; n < 3; ++n)
-            {
-              cf1[u][2 * n] = cf1[u][2 * n + 1] = 0.0;
+            for (int q = 0; q < 6; ++q) cf1[u][q] = 0.0;
+            // k outermost: the three n-tile accumulators advance together (independent MMA chains)
 #pragma unroll
-              for (int kk = 0; kk < 5; ++kk) dmma884(cf1[u][2 * n], cf1[u][2 * n + 1], a[kk], bf[n * 5 + kk]);
-            }
+            for (int kk = 0; kk < 5; ++kk)
+#pragma unroll
+              for (int n = 0; n < 3; ++n) dmma884(cf1[u][2 * n], cf1[u][2 * n + 1], a[kk], bf[n * 5 + kk]);
           }
         }
         else
@@ -930,12 +1200,12 @@ __global__ void __launch_bounds__(kTravThreads, 2)
             const unsigned bal = __ballot_sync(0xffffffffu, mine);
             one2[u] = ((bal >> (lane & ~3)) & 0xFu) == 0xFu;
 #pragma unroll
-            for (int n = 0; n < 3; ++n)
-            {
-              cf2[u][2 * n] = cf2[u][2 * n + 1] = 0.0;
+            for (int q = 0; q < 6; ++q) cf2[u][q] = 0.0;
+            // k outermost: the three n-tile accumulators advance together (independent MMA chains)
 #pragma unroll
-              for (int kk = 0; kk < 5; ++kk) dmma884(cf2[u][2 * n], cf2[u][2 * n + 1], a[kk], bf[n * 5 + kk]);
-            }
+            for (int kk = 0; kk < 5; ++kk)
+#pragma unroll
+              for (int n = 0; n < 3; ++n) dmma884(cf2[u][2 * n], cf2[u][2 * n + 1], a[kk], bf[n * 5 + kk]);
           }
         }
         else
