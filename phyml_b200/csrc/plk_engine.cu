@@ -719,7 +719,7 @@ static int launch_traverse_aa(plk_instance *inst, const OpDev *d_ops, int n_ops)
     CU_TRY(inst, cudaFuncSetAttribute(k_traverse_aa, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     inst->aa_attr_set = true;
   }
-  const int slots = inst->num_sms * 2;
+  const int slots = inst->num_sms;  // one 512-thread block per SM
   const long long cap = (long long)slots * kAaTileCap;
   const int       rounds = (int)((P + cap - 1) / cap);
   int             n_tiles = std::max(1, std::min(slots * rounds, (P + 7) / 8));
@@ -729,7 +729,7 @@ static int launch_traverse_aa(plk_instance *inst, const OpDev *d_ops, int n_ops)
   n_tiles = (P + tile_sites - 1) / tile_sites;
   const int       grid = std::min(n_tiles, slots);
   const long long code_delta = (long long)(inst->d_tipcodes - inst->d_tiprows);
-  k_traverse_aa<<<grid, kTravThreads, smem, inst->stream>>>(d_ops, n_ops, P, nc, tile_sites, n_tiles, inst->d_wght,
+  k_traverse_aa<<<grid, kAaThreads, smem, inst->stream>>>(d_ops, n_ops, P, nc, tile_sites, n_tiles, inst->d_wght,
                                                           inst->d_tipmask, code_delta, inst->apply_scaling);
   inst->launches++;
   CU_TRY(inst, cudaGetLastError());

@@ -970,8 +970,10 @@ __global__ void __launch_bounds__(kTravThreads, 2)
 // Same warp roles / TMA-mbarrier ring as k_traverse_dna; CLVs written by an update are re-read by
 // later updates of the same warp (different lanes: __syncwarp() after every update).
 constexpr int kAaStages = 3;
-constexpr int kAaU = 2;  // m-tiles (of 8 sites) per warp
-constexpr int kAaTileCap = kTravComputeWarps * 8 * kAaU;
+constexpr int kAaU = 1;  // m-tiles (of 8 sites) per warp (2 spills at 128 registers and is 40% slower)
+constexpr int kAaComputeWarps = 15;  // + 1 producer warp = 512 threads, ONE block per SM (128 registers)
+constexpr int kAaThreads = (kAaComputeWarps + 1) * 32;
+constexpr int kAaTileCap = kAaComputeWarps * 8 * kAaU;
 __host__ __device__ inline size_t aa_stage_bytes(int ncatg) { return 128 + 2 * (size_t)ncatg * 420 * sizeof(double); }
 
 // C fragment of a tip child: u[i] = sum_{j in mask} P[i][j] for the thread's output states
@@ -1015,7 +1017,7 @@ __device__ __forceinline__ void aa_tip_frag(const double *tpx /* [21][20] of thi
   }
 }
 
-__global__ void __launch_bounds__(kTravThreads, 2)
+__global__ void __launch_bounds__(kAaThreads, 1)
     k_traverse_aa(const OpDev *__restrict__ ops, int n_ops, int npat, int ncatg, int tile_sites, int n_tiles,
                   const double *__restrict__ wght, const uint32_t *__restrict__ tipmask, long long code_delta,
                   int apply_scaling)
@@ -1032,14 +1034,14 @@ __global__ void __launch_bounds__(kTravThreads, 2)
     for (int s = 0; s < S; ++s)
     {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], kTravComputeWarps);
+      mbar_init(&empty[s], kAaComputeWarps);
     }
   __syncthreads();
 
   const int       rounds = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const long long total_it = (long long)rounds * n_ops;
 
-  if (warp == kTravComputeWarps)
+  if (warp == kAaComputeWarps)
   {  // ---------------- producer warp
     for (long long base = 0; base < total_it; base += 32)
     {
@@ -1092,7 +1094,7 @@ __global__ void __launch_bounds__(kTravThreads, 2)
 #pragma unroll
     for (int u = 0; u < kAaU; ++u)
     {
-      const int ls = (u * kTravComputeWarps + warp) * 8 + g;
+      const int ls = (u * kAaComputeWarps + warp) * 8 + g;
       valid[u] = ls < n_sites;
       site[u] = base_site + (valid[u] ? ls : n_sites - 1);
       live[u] = valid[u] && (wght[site[u]] > DBL_MIN);
