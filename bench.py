@@ -245,13 +245,20 @@ def run_b200(args):
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_traverse_dna<4,2>" if ns == 4 else "k_partial(ns=%d)" % ns,
+            "roofline": {"bound": "hbm", "kernel": "k_traverse_dna<4,2>" if ns == 4 else ("k_traverse_aa (DMMA.8x8x4)" if ns == 20 else "k_partial_generic"),
                          "achieved": achieved, "peak": peak,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "algorithmic_bytes_per_eval": k1_bytes, "k1_ms_per_eval": k1_avg_ms,
                          "k1_launches_per_eval": None},
         }
+        if ns == 20:
+            # the 20-state path is the dense contraction on the FP64 tensor pipe: also report its flop rate
+            n_int = sum((0 if o.c1.is_tip else 1) + (0 if o.c2.is_tip else 1) for o in ops)
+            flops = 2.0 * 20 * 20 * ncatg * P * n_int            # useful MACs*2 of the P.x products
+            out["roofline"]["fp64_tensor"] = {"achieved_tflops": flops / (k1_avg_ms * 1e-3) / 1e12,
+                                              "nominal_peak_tflops": 40.0,
+                                              "note": "useful flops of the (20x20).(20xsites) contractions; MMA tiles are padded 20->24"}
         tr = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tr):
             try:
