@@ -379,7 +379,7 @@ int plk_create(const plk_config *cfg, plk_instance **out)
   CREATE_TRY(cudaStreamCreateWithFlags(&inst->stream, cudaStreamNonBlocking));
 
   const size_t P = (size_t)cfg->n_patterns;
-  inst->tip_stride = (P + 127) & ~(size_t)127;
+  inst->tip_stride = P;  // dense rows: the whole [n_tips][P] code matrix is one contiguous H2D copy
   inst->pmat_elems = (size_t)cfg->ncatg * cfg->ns * cfg->ns;
   inst->pmat_stride = inst->pmat_elems + (cfg->ns == 4 ? (size_t)cfg->ncatg * 64 : 0) +
                       (cfg->ns == 20 ? (size_t)cfg->ncatg * 420 : 0);
@@ -522,8 +522,12 @@ int plk_set_tip_codes(plk_instance *inst, int tip, const uint8_t *codes)
 int plk_set_all_tip_codes(plk_instance *inst, const uint8_t *codes, size_t host_stride)
 {
   ARG_CHECK(inst, codes && host_stride >= (size_t)inst->cfg.n_patterns, "plk_set_all_tip_codes: bad arguments");
-  CU_TRY(inst, cudaMemcpy2DAsync(inst->d_tipcodes, inst->tip_stride, codes, host_stride, inst->cfg.n_patterns,
-                                 inst->cfg.n_tips, cudaMemcpyHostToDevice, inst->stream));
+  if (host_stride == inst->tip_stride)
+    CU_TRY(inst, cudaMemcpyAsync(inst->d_tipcodes, codes, inst->tip_stride * inst->cfg.n_tips, cudaMemcpyHostToDevice,
+                                 inst->stream));
+  else
+    CU_TRY(inst, cudaMemcpy2DAsync(inst->d_tipcodes, inst->tip_stride, codes, host_stride, inst->cfg.n_patterns,
+                                   inst->cfg.n_tips, cudaMemcpyHostToDevice, inst->stream));
   inst->tiprows_dirty = true;
   return PLK_OK;
 }

@@ -183,6 +183,20 @@ def test_large_config_properties():
     assert abs(a - b) <= 1e-12 * abs(b)
 
 
+def test_many_updates_multi_chunk():
+    """A 3 000-taxon tree: 2 998 post-order + 5 996 pre-order updates in one plk_update_partials call,
+    i.e. more descriptors than one staging block holds (the fused launch is split, the register-forwarding
+    chain restarts at the chunk boundary) -- against the oracle."""
+    tree, m, pat = _synthetic(4, 3000, 48, 17, 0.02, mean_bl=0.05)
+    args = (tree.n_otu, pat.n_pattern, 4, 4, tree.n_clv_handles, tree.n_edges)
+    gpu, cpu = LkTree(tree, pat, m, Engine(*args)), LkTree(tree, pat, m, OracleBackend(*args))
+    for t in (gpu, cpu):
+        t.Set_Both_Sides(1)
+    assert abs(gpu.Lk() - cpu.Lk()) <= 1e-12 * abs(cpu.c_lnL)
+    for e in (0, tree.n_edges // 3, tree.n_edges - 1):
+        assert abs(gpu.Lk(e) - cpu.Lk(e)) <= 1e-12 * abs(cpu.c_lnL)
+
+
 def test_error_paths():
     from phyml_b200.engine import EngineError
     from phyml_b200.tree import Side
