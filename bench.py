@@ -169,7 +169,9 @@ def run_b200(args):
         evaluate()
     sampler = ClockSampler(local)
     sampler.start()
-    time.sleep(0.25)
+    t_wait = time.time()
+    while not sampler.rows and time.time() - t_wait < 15.0:   # nvidia-smi needs a moment to start
+        time.sleep(0.05)
     k1_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = eng.launch_count
@@ -182,7 +184,6 @@ def run_b200(args):
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count - launches0
     k1_ms = [a.elapsed_time(b) for a, b in k1_ev]
-    clocks = sampler.finish()
 
     # ---------------- end-to-end leg: host buffers in, lnL (+ per-site lnL) out, every step
     for _ in range(max(1, args.warmup // 2)):
@@ -200,6 +201,12 @@ def run_b200(args):
     g1.record(stream)
     barrier()
     e2e_ms = max(g0.elapsed_time(g1), (time.perf_counter() - t0) * 1e3)
+    # keep the GPU under the same load until the sampler has seen it (its period is 100 ms, a timed leg ~10 ms)
+    n_rows = len(sampler.rows)
+    t_wait = time.time()
+    while len(sampler.rows) < n_rows + 3 and time.time() - t_wait < 3.0:
+        evaluate()
+    clocks = sampler.finish()
     assert abs(lnl_e2e - lnl) <= 1e-12 * abs(lnl)
     assert abs(float(np.dot(h_site.numpy(), pat.wght)) - (lnl if world == 1 else float("nan"))) <= 1e-9 * abs(lnl) or world > 1
 
