@@ -73,6 +73,11 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
         self.proc = None
+        self.first = 0
+
+    def mark(self):
+        """Samples before this point (GPU idle) are not part of the statistics."""
+        self.first = len(self.rows)
 
     def run(self):
         try:
@@ -91,6 +96,7 @@ class ClockSampler(threading.Thread):
         if self.proc:
             self.proc.terminate()
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        self.rows = self.rows[self.first:] or self.rows
         sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
         if sm:
             out["sm_mhz"] = statistics.median(sm)
@@ -123,10 +129,11 @@ def run_b200(args):
     ns, ncatg, P, n = m.ns, m.ncatg, pat.n_pattern, tree.n_otu
     eng = Engine(n, P, ns, ncatg, tree.n_clv_handles, tree.n_edges, device=local)
     if world > 1:
-        # one NCCL communicator inside the engine: the all-reduce is enqueued on the engine stream
-        uid = [Engine.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        eng.comm_init(rank, world, uid[0])
+        # cross-GPU sum of the partial lnL: fused into the reduction kernel over NVLink peer memory
+        # (PLK_COMM=nccl selects the ncclAllReduce fallback)
+        from phyml_b200.sharding import init_engine_comm
+
+        init_engine_comm(eng, rank, world, mode=os.environ.get("PLK_COMM", "p2p"))
 
     ops = tree.post_order_ops()
     ops_packed = pack_ops(ops)
@@ -176,6 +183,7 @@ def run_b200(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = eng.launch_count
     barrier()
+    sampler.mark()
     e0.record(stream)
     for s in range(args.steps):
         lnl = evaluate(k1_ev[s])
@@ -184,6 +192,17 @@ def run_b200(args):
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count - launches0
     k1_ms = [a.elapsed_time(b) for a, b in k1_ev]
+    # keep the GPU under the same load until the sampler has seen it (its period is 100 ms, the timed leg ~10 ms);
+    # it is stopped before the e2e leg, whose many small driver calls an NVML poller would perturb
+    n_rows = len(sampler.rows)
+    t_wait = time.time()
+    while len(sampler.rows) < n_rows + 3 and time.time() - t_wait < 3.0:
+        # LOCAL work only (K0 + K1, no reduction): the number of iterations differs between ranks, so
+        # nothing in this loop may involve the cross-GPU exchange
+        eng.update_pmats(edges, lengths)
+        eng.update_partials(ops_packed)
+        eng.sync()
+    clocks = sampler.finish()
 
     # ---------------- end-to-end leg: host buffers in, lnL (+ per-site lnL) out, every step
     for _ in range(max(1, args.warmup // 2)):
@@ -201,12 +220,6 @@ def run_b200(args):
     g1.record(stream)
     barrier()
     e2e_ms = max(g0.elapsed_time(g1), (time.perf_counter() - t0) * 1e3)
-    # keep the GPU under the same load until the sampler has seen it (its period is 100 ms, a timed leg ~10 ms)
-    n_rows = len(sampler.rows)
-    t_wait = time.time()
-    while len(sampler.rows) < n_rows + 3 and time.time() - t_wait < 3.0:
-        evaluate()
-    clocks = sampler.finish()
     assert abs(lnl_e2e - lnl) <= 1e-12 * abs(lnl)
     assert abs(float(np.dot(h_site.numpy(), pat.wght)) - (lnl if world == 1 else float("nan"))) <= 1e-9 * abs(lnl) or world > 1
 
@@ -245,6 +258,7 @@ def run_b200(args):
             "config": {"workload": desc, "name": args.workload, "n_taxa": n, "sites_per_gpu": WORKLOADS[args.workload][2],
                        "patterns_per_gpu": P, "ns": ns, "ncatg": ncatg, "updates_per_eval": n - 2,
                        "parallelism": f"site-shard x{world}", "both_sides": False,
+                       "exchange": ("none" if world == 1 else os.environ.get("PLK_COMM", "p2p")),
                        "l2": "CLV working set %.2f GB per evaluation > 126 MB L2 (no flush needed)"
                              % ((n - 2) * P * ns * ncatg * 8 / 1e9)},
             "evals_per_s": args.steps / (ms * 1e-3), "lnL": lnl,

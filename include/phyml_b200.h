@@ -160,6 +160,12 @@ int plk_get_dot_prod(plk_instance *inst, double *dot_prod);
  * plk_comm_unique_id: rank 0 fills a 128-byte id that the host broadcasts to the other ranks. */
 int plk_comm_unique_id(void *id128);
 int plk_comm_init(plk_instance *inst, int rank, int world, const void *id128);
+/* Fused alternative (default of bench.py): the reduction kernels themselves post their partial sums into
+ * every rank's mailbox over NVLink peer memory (CUDA IPC) and add all ranks' partials in rank order --
+ * no extra launch, bitwise identical result on every rank.  Each rank exports a 64-byte IPC handle; the
+ * host gathers the `world` handles (rank order) and hands the array to every rank. */
+int plk_comm_p2p_export(plk_instance *inst, int world, void *handle64);
+int plk_comm_p2p_init(plk_instance *inst, int rank, int world, const void *handles);
 /* after plk_comm_init, plk_edge_lnl / _dlnl / _eigen return the ALL-RANK sum when enabled */
 int plk_comm_set_allreduce(plk_instance *inst, int enable);
 

@@ -117,6 +117,11 @@ struct plk_instance
 
   void *comm = nullptr;
   bool  allreduce = false;
+  // fused P2P exchange (CUDA IPC mailboxes over NVLink)
+  P2pSlot  *d_mbox = nullptr;        // this rank's mailbox [2][world]
+  P2pSlot **d_peers = nullptr;       // device array: every rank's mailbox as mapped here
+  std::vector<void *> ipc_opened;
+  bool      p2p = false;
   int   rank = 0, world = 1;
   double l_min = 1e-8, l_max = 100.0;  // host copy of mod->l_min / l_max (plk_set_model)
   int    trav_umax = 2;                // items per thread of the fused traversal kernel
@@ -255,6 +260,9 @@ ReduceOut make_reduce_out(plk_instance *inst)
   ro.host_out = inst->h_result_dev;
   ro.seq = ++inst->seq;
   ro.publish = inst->allreduce ? 0 : 1;
+  ro.peers = inst->p2p ? inst->d_peers : nullptr;
+  ro.rank = inst->rank;
+  ro.world = inst->p2p ? inst->world : 1;
   return ro;
 }
 
@@ -432,6 +440,9 @@ void plk_destroy(plk_instance *inst)
   cudaSetDevice(inst->cfg.device);
   if (inst->stream) cudaStreamSynchronize(inst->stream);
   if (inst->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(inst->comm);
+  for (void *p : inst->ipc_opened) cudaIpcCloseMemHandle(p);
+  cudaFree(inst->d_mbox);
+  cudaFree(inst->d_peers);
   for (double *p : inst->clv) cudaFree(p);
   for (int *p : inst->scale) cudaFree(p);
   cudaFree(inst->d_wght);
@@ -1170,6 +1181,53 @@ int plk_comm_init(plk_instance *inst, int rank, int world, const void *id128)
   inst->rank = rank;
   inst->world = world;
   inst->allreduce = true;
+  return PLK_OK;
+}
+
+// ---- fused P2P exchange: mailboxes shared with CUDA IPC, written by the reduction kernels themselves ----
+int plk_comm_p2p_export(plk_instance *inst, int world, void *handle64)
+{
+  ARG_CHECK(inst, handle64 && world >= 1 && world <= 64, "plk_comm_p2p_export: bad arguments");
+  if (!inst->d_mbox)
+  {
+    int rc = dev_alloc(inst, &inst->d_mbox, (size_t)2 * world);
+    if (rc) return rc;
+    CU_TRY(inst, cudaMemset(inst->d_mbox, 0, sizeof(P2pSlot) * 2 * world));
+  }
+  cudaIpcMemHandle_t h;
+  CU_TRY(inst, cudaIpcGetMemHandle(&h, inst->d_mbox));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memcpy(handle64, &h, 64);
+  inst->world = world;
+  return PLK_OK;
+}
+
+int plk_comm_p2p_init(plk_instance *inst, int rank, int world, const void *handles)
+{
+  ARG_CHECK(inst, handles && inst->d_mbox && world == inst->world && rank >= 0 && rank < world,
+            "plk_comm_p2p_init: call plk_comm_p2p_export first");
+  std::vector<P2pSlot *> peers(world, nullptr);
+  for (int q = 0; q < world; ++q)
+  {
+    if (q == rank)
+    {
+      peers[q] = inst->d_mbox;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char *)handles + (size_t)q * 64, 64);
+    void *p = nullptr;
+    CU_TRY(inst, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    inst->ipc_opened.push_back(p);
+    peers[q] = (P2pSlot *)p;
+  }
+  int rc = dev_alloc(inst, &inst->d_peers, (size_t)world);
+  if (rc) return rc;
+  CU_TRY(inst, cudaMemcpy(inst->d_peers, peers.data(), sizeof(P2pSlot *) * world, cudaMemcpyHostToDevice));
+  inst->rank = rank;
+  inst->world = world;
+  inst->p2p = true;
+  inst->allreduce = false;  // the exchange now happens inside the reduction kernel
   return PLK_OK;
 }
 

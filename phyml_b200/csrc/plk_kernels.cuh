@@ -1359,7 +1359,28 @@ struct ReduceOut
   volatile ResultHost *host_out;
   unsigned long long   seq;
   int                  publish;   // 1: write host_out here; 0: an all-reduce + k_publish follow
+  // fused cross-GPU sum over NVLink peer memory (world > 1, p2p mode): every rank owns a mailbox
+  // [2 parities][world senders] of P2pSlot; peers[q] is rank q's mailbox mapped into this process.
+  struct P2pSlot     **peers;
+  int                  rank, world;
 };
+
+struct __align__(32) P2pSlot
+{
+  double             v[3];
+  unsigned long long seq;
+};
+
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v)
+{
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 
 // Deterministic reduction of up to 2 running sums in ONE launch: fixed shuffle tree per warp, fixed
 // warp order per block, per-block partials to global memory; the block that finishes last (atomic
@@ -1415,9 +1436,36 @@ __device__ __forceinline__ void block_reduce_finish(double (&v)[NV], int warn, c
     double r[2] = {0.0, 0.0};
     for (int k = 0; k < NV; ++k)
       for (int t = 0; t < (int)blockDim.x; ++t) r[k] += sfin[k][t];
-    const int w = *ro.warn_flag;
+    int w = *ro.warn_flag;
     *ro.warn_flag = 0;
     *ro.ticket = 0u;
+    if (ro.world > 1 && ro.peers)
+    {
+      // reduction + collective in one kernel: post this rank's partial into every rank's mailbox
+      // (remote stores over NVLink), wait for all ranks, add in RANK ORDER (bitwise identical result
+      // on every rank).  Two parity slots: a rank can be at most one evaluation ahead of its readers.
+      const int par = (int)(ro.seq & 1ull);
+      for (int q = 0; q < ro.world; ++q)
+      {
+        P2pSlot *slot = ro.peers[q] + par * ro.world + ro.rank;
+        slot->v[0] = r[0];
+        slot->v[1] = r[1];
+        slot->v[2] = (double)w;
+        st_release_sys_u64(&slot->seq, ro.seq);
+      }
+      double acc[3] = {0.0, 0.0, 0.0};
+      for (int q = 0; q < ro.world; ++q)
+      {
+        const P2pSlot *slot = ro.peers[ro.rank] + par * ro.world + q;
+        while (ld_acquire_sys_u64(&slot->seq) != ro.seq) __nanosleep(40);
+        acc[0] += slot->v[0];
+        acc[1] += slot->v[1];
+        acc[2] += slot->v[2];
+      }
+      r[0] = acc[0];
+      r[1] = acc[1];
+      w = acc[2] > 0.0 ? 1 : 0;
+    }
     ro.dev_out[0] = r[0];
     ro.dev_out[1] = r[1];
     ro.dev_out[2] = (double)w;

@@ -45,6 +45,7 @@ EXPORTS = [
     "plk_set_pmat", "plk_get_pmat", "plk_update_partials", "plk_edge_lnl", "plk_eigen_lr",
     "plk_edge_lnl_dlnl", "plk_edge_lnl_eigen", "plk_get_clv", "plk_set_clv", "plk_get_site_lnl",
     "plk_get_dot_prod", "plk_comm_unique_id", "plk_comm_init", "plk_comm_set_allreduce",
+    "plk_comm_p2p_export", "plk_comm_p2p_init",
     "plk_launch_count", "plk_device_bytes", "plk_stream", "plk_version",
 ]
 
@@ -89,6 +90,8 @@ def load_library() -> C.CDLL:
     lib.plk_comm_unique_id.argtypes = [vp]
     lib.plk_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
     lib.plk_comm_set_allreduce.argtypes = [vp, C.c_int]
+    lib.plk_comm_p2p_export.argtypes = [vp, C.c_int, vp]
+    lib.plk_comm_p2p_init.argtypes = [vp, C.c_int, C.c_int, vp]
     lib.plk_launch_count.argtypes = [vp]
     lib.plk_launch_count.restype = C.c_longlong
     lib.plk_device_bytes.argtypes = [vp]
@@ -295,6 +298,16 @@ class Engine:
     def comm_init(self, rank: int, world: int, unique_id: bytes):
         assert len(unique_id) == 128
         self._ck(self.lib.plk_comm_init(self.h, rank, world, C.c_char_p(unique_id)))
+
+    def comm_p2p_export(self, world: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._ck(self.lib.plk_comm_p2p_export(self.h, world, buf))
+        return buf.raw
+
+    def comm_p2p_init(self, rank: int, world: int, handles: Sequence[bytes]):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * world
+        self._ck(self.lib.plk_comm_p2p_init(self.h, rank, world, C.c_char_p(blob)))
 
     def comm_set_allreduce(self, enable: bool):
         self._ck(self.lib.plk_comm_set_allreduce(self.h, int(enable)))

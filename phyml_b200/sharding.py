@@ -29,12 +29,21 @@ def dist_reduce_fn(group=None) -> Callable[[Sequence[float]], Sequence[float]]:
     return reduce
 
 
-def init_engine_comm(engine, rank: int, world: int, group=None) -> None:
-    """Create the engine-internal NCCL communicator; the 128-byte id travels over `group`."""
+def init_engine_comm(engine, rank: int, world: int, group=None, mode: str = "p2p") -> None:
+    """Wire the engine's cross-GPU sum.  mode "p2p": mailboxes over NVLink peer memory written by the
+    reduction kernels themselves (CUDA IPC handles travel over `group`); mode "nccl": an ncclAllReduce
+    enqueued behind the reduction kernel (the 128-byte unique id travels over `group`)."""
     import torch.distributed as dist
 
     from .engine import Engine
 
+    if mode == "p2p":
+        mine = engine.comm_p2p_export(world)
+        handles = [None] * world
+        dist.all_gather_object(handles, mine, group=group)
+        engine.comm_p2p_init(rank, world, handles)
+        dist.barrier(group=group)
+        return
     uid = [Engine.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0, group=group)
     engine.comm_init(rank, world, uid[0])

@@ -1,0 +1,85 @@
+"""Two-GPU test of the site-sharded engine (skipped with fewer than 2 devices): each rank evaluates its
+block of patterns; the cross-GPU sum happens inside the reduction kernel over NVLink peer memory
+(plk_comm_p2p_*) or through the in-engine ncclAllReduce (plk_comm_init).  Both must return, on every rank,
+the single-GPU value; the P2P result must be bitwise identical across ranks (rank-order addition)."""
+import os
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _case():
+    from phyml_b200 import alignment, model as pmodel
+    from phyml_b200.tree import Tree
+
+    tree = Tree.random(18, seed=31)
+    m = pmodel.gtr(alpha=0.5)
+    pat = alignment.compress(alignment.simulate(tree, m, 6001, seed=32, ambiguity=0.02), 4)
+    return tree, m, pat
+
+
+def _worker(rank, world, port, mode, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from phyml_b200.engine import Engine
+    from phyml_b200.lk import LkTree
+    from phyml_b200.sharding import init_engine_comm
+
+    tree, m, pat = _case()
+    sh = pat.shard(rank, world)
+    eng = Engine(tree.n_otu, sh.n_pattern, 4, 4, tree.n_clv_handles, tree.n_edges, device=rank)
+    init_engine_comm(eng, rank, world, mode=mode)
+    t = LkTree(tree, sh, m, eng)
+    lnl = t.Lk()
+    t.Set_Update_Eigen_Lr(1)
+    t.Lk(3)
+    t.Set_Update_Eigen_Lr(0)
+    t.dLk(0.05, 3)
+    q.put((rank, lnl, t.c_lnL, t.c_dlnL))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["p2p", "nccl"])
+def test_two_gpu_sharded_lnl(mode):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    from phyml_b200.engine import Engine
+    from phyml_b200.lk import LkTree
+
+    tree, m, pat = _case()
+    ref = LkTree(tree, pat, m, Engine(tree.n_otu, pat.n_pattern, 4, 4, tree.n_clv_handles, tree.n_edges))
+    ref_lnl = ref.Lk()
+    ref.Set_Update_Eigen_Lr(1)
+    ref.Lk(3)
+    ref.Set_Update_Eigen_Lr(0)
+    ref.dLk(0.05, 3)
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 300
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in range(2))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for r in res:
+        assert abs(r[1] - ref_lnl) <= 1e-12 * abs(ref_lnl)
+        assert abs(r[2] - ref.c_lnL) <= 1e-12 * abs(ref.c_lnL)
+        assert abs(r[3] - ref.c_dlnL) <= 1e-9 * max(1.0, abs(ref.c_dlnL))
+    if mode == "p2p":
+        assert res[0][1:] == res[1][1:], "rank-order addition must give bitwise identical results on all ranks"
