@@ -38,6 +38,7 @@ def _worker(rank, world, port, mode, q):
     eng = Engine(tree.n_otu, sh.n_pattern, 4, 4, tree.n_clv_handles, tree.n_edges, device=rank)
     init_engine_comm(eng, rank, world, mode=mode)
     t = LkTree(tree, sh, m, eng)
+    t.Set_Both_Sides(1)
     lnl = t.Lk()
     t.Set_Update_Eigen_Lr(1)
     t.Lk(3)
@@ -61,6 +62,7 @@ def test_two_gpu_sharded_lnl(mode):
 
     tree, m, pat = _case()
     ref = LkTree(tree, pat, m, Engine(tree.n_otu, pat.n_pattern, 4, 4, tree.n_clv_handles, tree.n_edges))
+    ref.Set_Both_Sides(1)
     ref_lnl = ref.Lk()
     ref.Set_Update_Eigen_Lr(1)
     ref.Lk(3)
