@@ -42,7 +42,7 @@ class Model:
 
     def pmat(self, l: float) -> np.ndarray:
         """Host restatement of Update_PMat_At_Given_Edge + PMat_Empirical (numpy; for simulation
-        only -- the product computes P on the device, the parity oracle is oracle/plk_oracle.c)."""
+        only -- the product computes P on the device, K0)."""
         out = np.empty((self.ncatg, self.ns, self.ns))
         for c in range(self.ncatg):
             ln = min(max(max(0.0, l) * self.rates[c] * self.br_len_mult, self.l_min), self.l_max)
