@@ -390,7 +390,7 @@ int plk_create(const plk_config *cfg, plk_instance **out)
   inst->tip_stride = P;  // dense rows: the whole [n_tips][P] code matrix is one contiguous H2D copy
   inst->pmat_elems = (size_t)cfg->ncatg * cfg->ns * cfg->ns;
   inst->pmat_stride = inst->pmat_elems + (cfg->ns == 4 ? (size_t)cfg->ncatg * 64 : 0) +
-                      (cfg->ns == 20 ? (size_t)cfg->ncatg * 420 : 0);
+                      (cfg->ns == 20 ? (size_t)cfg->ncatg * (420 + 480) : 0);
   inst->clv.assign(cfg->n_clv, nullptr);
   inst->scale.assign(cfg->n_clv, nullptr);
 
@@ -670,6 +670,12 @@ int plk_set_pmat(plk_instance *inst, int pmat, const double *P)
         for (int j = 1; j < 20; ++j) a = a + Pc[i * 20 + j];
         TX[20 * 20 + i] = a;
         for (int sidx = 0; sidx < 20; ++sidx) TX[sidx * 20 + i] = Pc[i * 20 + sidx];
+      }
+      double *PF = rec.data() + inst->pmat_elems + (size_t)inst->cfg.ncatg * 420 + (size_t)c * 480;
+      for (int q = 0; q < 480; ++q)
+      {
+        const int j = q >> 5, ln = q & 31, n = j / 5, kk = j % 5, gg = ln >> 2, tt = ln & 3;
+        PF[q] = (n * 8 + gg < 20) ? Pc[(n * 8 + gg) * 20 + kk * 4 + tt] : 0.0;
       }
     }
   }
@@ -955,11 +961,15 @@ int plk_update_partials(plk_instance *inst, int n_ops, const plk_op *ops)
             d.P1 += inst->pmat_elems;
             d.t1 = inst->d_tiprows + (size_t)x.tip * inst->tip_stride;
           }
+          else if (fused_aa)
+            d.P1 += inst->pmat_elems + (size_t)nc * 420;  // fragment-ordered P
           if (y.tip >= 0)
           {
             d.P2 += inst->pmat_elems;
             d.t2 = inst->d_tiprows + (size_t)y.tip * inst->tip_stride;
           }
+          else if (fused_aa)
+            d.P2 += inst->pmat_elems + (size_t)nc * 420;
         }
         if (fused_aa) kind = (x.tip >= 0 ? 1 : 0) | (y.tip >= 0 ? 2 : 0);
         d.flags = kind;

@@ -236,6 +236,14 @@ __global__ void k_pmat(const PmatJob *__restrict__ jobs, const ModelDev *__restr
       for (int j = 1; j < ns; ++j) a = a + raw[e * ns + j];
       TX[20 * ns + e] = a;
     }
+    // Pf[c][j = n*5+kk][lane = g*4+t] = P[c][8n+g][4kk+t] (0 for rows >= 20): the B fragments of
+    // k_traverse_aa in the order its lanes read them (conflict-free LDS.64, no address arithmetic)
+    double *PF = jobs[job].P + (size_t)ncatg * (nn + 420) + (size_t)c * 480;
+    for (int q = e; q < 480; q += blockDim.x)
+    {
+      const int j = q >> 5, ln = q & 31, n = j / 5, kk = j % 5, gg = ln >> 2, tt = ln & 3;
+      PF[q] = (n * 8 + gg < 20) ? raw[(n * 8 + gg) * 20 + kk * 4 + tt] : 0.0;
+    }
   }
   else if (with_tip_table)
   {  // ns == 4: TP[c][tip_row4(mask)][i] = sum_{j in mask} P[c][i][j], ascending j (a tip child's vector)
@@ -974,7 +982,7 @@ constexpr int kAaU = 1;  // m-tiles (of 8 sites) per warp (2 spills at 128 regis
 constexpr int kAaComputeWarps = 15;  // + 1 producer warp = 512 threads, ONE block per SM (128 registers)
 constexpr int kAaThreads = (kAaComputeWarps + 1) * 32;
 constexpr int kAaTileCap = kAaComputeWarps * 8 * kAaU;
-__host__ __device__ inline size_t aa_stage_bytes(int ncatg) { return 128 + 2 * (size_t)ncatg * 420 * sizeof(double); }
+__host__ __device__ inline size_t aa_stage_bytes(int ncatg) { return 128 + 2 * (size_t)ncatg * 480 * sizeof(double); }
 
 // C fragment of a tip child: u[i] = sum_{j in mask} P[i][j] for the thread's output states
 __device__ __forceinline__ void aa_tip_frag(const double *tpx /* [21][20] of this category */, int row, uint32_t mask,
@@ -1026,8 +1034,8 @@ __global__ void __launch_bounds__(kAaThreads, 1)
   extern __shared__ __align__(128) unsigned char aa_smem[];
   __shared__ __align__(8) uint64_t   full[S], empty[S];
   const size_t   stage_bytes = aa_stage_bytes(ncatg);
-  const uint32_t PB = (uint32_t)(ncatg * 400 * sizeof(double));
-  const uint32_t TB = (uint32_t)(ncatg * 420 * sizeof(double));
+  const uint32_t PB = (uint32_t)(ncatg * 480 * sizeof(double));  // fragment-ordered P
+  const uint32_t TB = (uint32_t)(ncatg * 420 * sizeof(double));  // transposed tip table
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0)
@@ -1072,7 +1080,7 @@ __global__ void __launch_bounds__(kAaThreads, 1)
           mbar_expect_tx(&full[s], (uint32_t)sizeof(OpDev) + b1 + b2);
           tma_bulk_g2s(stg, ops + (it % n_ops), (uint32_t)sizeof(OpDev), &full[s]);
           tma_bulk_g2s(stg + 128, (const void *)a1, b1, &full[s]);
-          tma_bulk_g2s(stg + 128 + (size_t)ncatg * 420 * sizeof(double), (const void *)a2, b2, &full[s]);
+          tma_bulk_g2s(stg + 128 + (size_t)ncatg * 480 * sizeof(double), (const void *)a2, b2, &full[s]);
         }
         __syncwarp();
       }
@@ -1108,7 +1116,7 @@ __global__ void __launch_bounds__(kAaThreads, 1)
       mbar_wait(&full[s], ph);
       const OpDev  &op = *reinterpret_cast<const OpDev *>(stg);
       const double *M1 = reinterpret_cast<const double *>(stg + 128);
-      const double *M2 = M1 + (size_t)ncatg * 420;
+      const double *M2 = M1 + (size_t)ncatg * 480;
       const double *c1 = op.c1, *c2 = op.c2;
       const bool    tip1 = (c1 == nullptr), tip2 = (c2 == nullptr);
       double *const dst = op.dst;
@@ -1146,13 +1154,10 @@ __global__ void __launch_bounds__(kAaThreads, 1)
         // ---- child 1
         if (!tip1)
         {
-          double bf[15];
-          const double *P = M1 + (size_t)c * 400;
+          double        bf[15];
+          const double *Pf = M1 + (size_t)c * 480 + lane;
 #pragma unroll
-          for (int n = 0; n < 3; ++n)
-#pragma unroll
-            for (int kk = 0; kk < 5; ++kk)
-              bf[n * 5 + kk] = (n * 8 + g < 20) ? P[(n * 8 + g) * 20 + kk * 4 + t] : 0.0;
+          for (int j = 0; j < 15; ++j) bf[j] = Pf[j * 32];
 #pragma unroll
           for (int u = 0; u < kAaU; ++u)
           {
@@ -1184,13 +1189,10 @@ __global__ void __launch_bounds__(kAaThreads, 1)
         // ---- child 2
         if (!tip2)
         {
-          double bf[15];
-          const double *P = M2 + (size_t)c * 400;
+          double        bf[15];
+          const double *Pf = M2 + (size_t)c * 480 + lane;
 #pragma unroll
-          for (int n = 0; n < 3; ++n)
-#pragma unroll
-            for (int kk = 0; kk < 5; ++kk)
-              bf[n * 5 + kk] = (n * 8 + g < 20) ? P[(n * 8 + g) * 20 + kk * 4 + t] : 0.0;
+          for (int j = 0; j < 15; ++j) bf[j] = Pf[j * 32];
 #pragma unroll
           for (int u = 0; u < kAaU; ++u)
           {
