@@ -134,6 +134,12 @@ struct plk_instance
 
   // scheduling scratch
   std::vector<int> lvl_write, lvl_read, op_level;
+  bool fused_dna = false, fused_aa = false;
+  // descriptor cache: a repeated identical op list (Lk(NULL) on an unchanged topology) is launched
+  // straight from the resolved descriptors of the previous call
+  std::vector<plk_op> cache_ops;
+  OpDev             *d_ops_cache = nullptr;
+  unsigned long long alloc_epoch = 0, cache_epoch = ~0ull;
 };
 
 #define CU_TRY(inst, call)                                                                         \
@@ -184,6 +190,7 @@ int ensure_clv(plk_instance *inst, int h)
   if (inst->clv[h]) return PLK_OK;
   int rc = dev_alloc(inst, &inst->clv[h], clv_elems(inst) + 4);
   if (rc) return rc;
+  inst->alloc_epoch++;
   rc = dev_alloc(inst, &inst->scale[h], (size_t)inst->cfg.n_patterns);
   if (rc) return rc;
   // zero-weight patterns are never written by K1 (avx.c:515-520): start from defined contents
@@ -350,10 +357,10 @@ int plk_create(const plk_config *cfg, plk_instance **out)
   inst->cfg = *cfg;
   inst->apply_scaling = (cfg->flags & PLK_FLAG_NO_SCALING) ? 0 : 1;
   {  // the blocked layout goes with the fused kernels; the generic kernel keeps the reference's layout
-    const int  nc = cfg->ncatg;
-    const bool fdna = (cfg->ns == 4) && (nc == 1 || nc == 2 || nc == 4 || nc == 8);
-    const bool faa = (cfg->ns == 20) && nc <= 8 && !getenv("PLK_AA_GENERIC");
-    inst->blocked = (fdna || faa) ? 1 : 0;
+    const int nc = cfg->ncatg;
+    inst->fused_dna = (cfg->ns == 4) && (nc == 1 || nc == 2 || nc == 4 || nc == 8);
+    inst->fused_aa = (cfg->ns == 20) && nc <= 8 && !getenv("PLK_AA_GENERIC");
+    inst->blocked = (inst->fused_dna || inst->fused_aa) ? 1 : 0;
   }
   auto fail = [&](int rc) {
     g_create_error = inst->err;
@@ -458,6 +465,7 @@ void plk_destroy(plk_instance *inst)
   cudaFree(inst->d_fact);
   cudaFree(inst->d_dot_prod);
   cudaFree(inst->d_tmp_clv);
+  cudaFree(inst->d_ops_cache);
   cudaFree(inst->d_partials);
   cudaFree(inst->d_warn);
   cudaFree(inst->d_ticket);
@@ -843,8 +851,7 @@ int plk_update_partials(plk_instance *inst, int n_ops, const plk_op *ops)
   if (n_ops == 0) return PLK_OK;
   const int  nclv = inst->cfg.n_clv;
   const int  nc = inst->cfg.ncatg;
-  const bool fused_dna = (inst->cfg.ns == 4) && (nc == 1 || nc == 2 || nc == 4 || nc == 8);
-  const bool fused_aa = (inst->cfg.ns == 20) && nc <= 8 && !getenv("PLK_AA_GENERIC");
+  const bool fused_dna = inst->fused_dna, fused_aa = inst->fused_aa;
   const bool fused = fused_dna || fused_aa;
   if (fused && inst->tiprows_dirty)
   {
@@ -859,6 +866,16 @@ int plk_update_partials(plk_instance *inst, int n_ops, const plk_op *ops)
     CU_TRY(inst, cudaGetLastError());
     inst->tiprows_dirty = false;
   }
+  const int per_slot = (int)(kStageBytes / sizeof(OpDev));
+  auto launch_fused = [&](const OpDev *d_ops, int n) {
+    return (fused_dna && inst->dna_mma && nc <= 4) ? launch_traverse_mma(inst, d_ops, n)
+           : fused_dna                             ? launch_traverse(inst, d_ops, n)
+                                                   : launch_traverse_aa(inst, d_ops, n);
+  };
+  if (fused && inst->d_ops_cache && inst->cache_epoch == inst->alloc_epoch && (int)inst->cache_ops.size() == n_ops &&
+      memcmp(inst->cache_ops.data(), ops, sizeof(plk_op) * (size_t)n_ops) == 0)
+    return launch_fused(inst->d_ops_cache, n_ops);  // same list as last time: descriptors are still valid
+
   // dependency levels: an op runs after the last writer of each operand it reads, after the last
   // reader of the buffer it overwrites and after the last writer of that buffer (RAW, WAR, WAW)
   inst->lvl_write.assign(nclv, -1);
@@ -907,7 +924,6 @@ int plk_update_partials(plk_instance *inst, int n_ops, const plk_op *ops)
     for (int l = 0; l <= max_level; ++l) cnt[l + 1] += cnt[l];
     for (int i = 0; i < n_ops; ++i) order[cnt[inst->op_level[i]]++] = i;
   }
-  const int per_slot = (int)(kStageBytes / sizeof(OpDev));
   std::vector<OpDev> host;
   host.reserve(std::min(n_ops, per_slot));
   int pos = 0;
@@ -982,12 +998,22 @@ int plk_update_partials(plk_instance *inst, int n_ops, const plk_op *ops)
     void *d = nullptr;
     int   rc = stage_upload(inst, host.data(), host.size() * sizeof(OpDev), &d);
     if (rc) return rc;
+    if (fused && n_ops <= per_slot && n_ops >= 8)
+    {  // remember the resolved descriptors of a whole-list launch (a traversal) for the next identical call
+      if (!inst->d_ops_cache)
+      {
+        rc = dev_alloc(inst, &inst->d_ops_cache, (size_t)per_slot);
+        if (rc) return rc;
+      }
+      CU_TRY(inst, cudaMemcpyAsync(inst->d_ops_cache, d, host.size() * sizeof(OpDev), cudaMemcpyDeviceToDevice,
+                                   inst->stream));
+      inst->cache_ops.assign(ops, ops + n_ops);
+      inst->cache_epoch = inst->alloc_epoch;
+    }
     for (auto &lc : launches)
     {
-      rc = (fused_dna && inst->dna_mma && nc <= 4) ? launch_traverse_mma(inst, (const OpDev *)d + lc.first, lc.second)
-           : fused_dna ? launch_traverse(inst, (const OpDev *)d + lc.first, lc.second)
-           : fused_aa ? launch_traverse_aa(inst, (const OpDev *)d + lc.first, lc.second)
-                      : launch_level_generic(inst, (const OpDev *)d + lc.first, lc.second);
+      rc = fused ? launch_fused((const OpDev *)d + lc.first, lc.second)
+                 : launch_level_generic(inst, (const OpDev *)d + lc.first, lc.second);
       if (rc) return rc;
     }
   }
