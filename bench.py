@@ -357,9 +357,10 @@ def run_reference(args):
     m = pmodel.gtr(alpha=0.5) if ns == 4 else pmodel.lg_from_fixture(alpha=0.5)
     cores = os.cpu_count() or 1
     # bounded sample: every host core gets its own block of columns of the workload's shape (sites are
-    # independent, the reference is single-threaded: one process per core); 3 000 columns per core keeps a
-    # process's likelihood arena near 115 MB and warmup+steps evaluations within a minute or two
-    per_core = 3000 if ns == 4 else 600
+    # independent, the reference is single-threaded: one process per core).  1 000 columns per core keeps a
+    # process's likelihood arena near 38 MB: measured on the 128-core GPU-box host this is the reference's
+    # best case (2.2e8 updates/s; 3 000 columns per core drop to 1.6e8, memory-bandwidth bound)
+    per_core = 1000 if ns == 4 else 200
     budget = int(1.5e7 * 90 / max(1, (args.steps + args.warmup)) / (n_taxa - 2))   # ~90 s at 1.5e7 updates/s/core
     per_core = max(200, min(per_core, budget))
     codes = alignment.simulate(tree, m, per_core * cores, seed=1000)
