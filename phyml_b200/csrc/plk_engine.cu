@@ -1028,12 +1028,25 @@ int plk_edge_lnl(plk_instance *inst, plk_side left, plk_side rght, int pmat, dou
   rc = check_side(inst, rght, true);
   if (rc) return rc;
   ARG_CHECK(inst, pmat >= 0 && pmat < inst->cfg.n_pmat && lnl, "plk_edge_lnl: bad arguments");
-  const int grid = reduce_grid(inst, 128);
-  k_edge_lnl<<<grid, 128, 0, inst->stream>>>(side_dev(inst, left), side_dev(inst, rght),
-                                             inst->d_pmat + (size_t)pmat * inst->pmat_stride, inst->d_model,
-                                             inst->cfg.n_patterns, inst->cfg.ns, inst->cfg.ncatg, inst->d_wght,
-                                             inst->d_invar, inst->d_tipmask, inst->d_site_lnl, inst->d_site_lk,
-                                             inst->d_site_lk_cat, inst->d_fact, make_reduce_out(inst), inst->blocked);
+  if (inst->fused_dna && inst->cfg.ncatg == 4)
+  {  // coalesced 4-state kernel on the blocked layout: thread per (site, category)
+    const int groups = (inst->cfg.n_patterns + 7) / 8;
+    const int grid = std::max(1, std::min((groups + 3) / 4, std::min(kMaxReduceBlocks, inst->num_sms * 16)));
+    k_edge_lnl_dna<4><<<grid, 128, 0, inst->stream>>>(side_dev(inst, left), side_dev(inst, rght),
+                                                      inst->d_pmat + (size_t)pmat * inst->pmat_stride, inst->d_model,
+                                                      inst->cfg.n_patterns, inst->d_wght, inst->d_invar, inst->d_tipmask,
+                                                      inst->d_site_lnl, inst->d_site_lk, inst->d_site_lk_cat,
+                                                      inst->d_fact, make_reduce_out(inst));
+  }
+  else
+  {
+    const int grid = reduce_grid(inst, 128);
+    k_edge_lnl<<<grid, 128, 0, inst->stream>>>(side_dev(inst, left), side_dev(inst, rght),
+                                               inst->d_pmat + (size_t)pmat * inst->pmat_stride, inst->d_model,
+                                               inst->cfg.n_patterns, inst->cfg.ns, inst->cfg.ncatg, inst->d_wght,
+                                               inst->d_invar, inst->d_tipmask, inst->d_site_lnl, inst->d_site_lk,
+                                               inst->d_site_lk_cat, inst->d_fact, make_reduce_out(inst), inst->blocked);
+  }
   inst->launches++;
   CU_TRY(inst, cudaGetLastError());
   inst->site_valid = true;
@@ -1072,10 +1085,21 @@ static int run_k4(plk_instance *inst, double l, int deriv, double *lnl, double *
     inst->err = "plk_edge_lnl_dlnl / _eigen called before plk_eigen_lr (update_eigen_lr)";
     return PLK_ERR_STATE;
   }
-  const int grid = reduce_grid(inst, 128);
-  k_lnl_dlnl<<<grid, 128, 0, inst->stream>>>(inst->d_dot_prod, inst->d_fact, inst->d_model, l, deriv,
-                                             inst->cfg.n_patterns, inst->cfg.ns, inst->cfg.ncatg, inst->d_wght,
-                                             inst->d_invar, inst->d_site_lnl, make_reduce_out(inst));
+  if (inst->cfg.ns == 4 && inst->cfg.ncatg == 4)
+  {
+    const int groups = (inst->cfg.n_patterns + 7) / 8;
+    const int grid = std::max(1, std::min((groups + 3) / 4, std::min(kMaxReduceBlocks, inst->num_sms * 16)));
+    k_lnl_dlnl_dna<4><<<grid, 128, 0, inst->stream>>>(inst->d_dot_prod, inst->d_fact, inst->d_model, l, deriv,
+                                                      inst->cfg.n_patterns, inst->d_wght, inst->d_invar,
+                                                      inst->d_site_lnl, make_reduce_out(inst));
+  }
+  else
+  {
+    const int grid = reduce_grid(inst, 128);
+    k_lnl_dlnl<<<grid, 128, 0, inst->stream>>>(inst->d_dot_prod, inst->d_fact, inst->d_model, l, deriv,
+                                               inst->cfg.n_patterns, inst->cfg.ns, inst->cfg.ncatg, inst->d_wght,
+                                               inst->d_invar, inst->d_site_lnl, make_reduce_out(inst));
+  }
   inst->launches++;
   CU_TRY(inst, cudaGetLastError());
   return finish_reduction(inst, lnl, dlnl, warn);

@@ -1632,6 +1632,248 @@ __global__ void __launch_bounds__(128)
 }
 
 // ------------------------------------------------------------------------------------------------
+// K2, 4 states: thread per (site, category) on the blocked layout (the warp reads 1 KB contiguous);
+// lane map as in k_traverse_dna (8 lanes per category), category terms gathered to the category-0
+// lane with shuffles and added in category order, i.e. the same arithmetic as k_edge_lnl.
+template <int NCATG>
+__global__ void __launch_bounds__(128)
+    k_edge_lnl_dna(SideDev left, SideDev rght, const double *__restrict__ P, const ModelDev *__restrict__ mod, int npat,
+                   const double *__restrict__ wght, const short *__restrict__ invar,
+                   const uint32_t *__restrict__ tipmask, double *__restrict__ site_lnl,
+                   double *__restrict__ site_lk_out, double *__restrict__ site_lk_cat, int *__restrict__ fact_sum_scale,
+                   ReduceOut ro)
+{
+  constexpr int SW = 32 / NCATG;
+  const int     lane = threadIdx.x & 31, cat = lane / SW;
+  const int     warps_per_block = blockDim.x >> 5, warp = threadIdx.x >> 5;
+  double        p[16], pi[4];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) p[q] = P[cat * 16 + q];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) pi[q] = mod->pi[q];
+  const double wc = mod->probs[cat];
+  double       acc[1] = {0.0};
+  int          warn = 0;
+  const int    groups = (npat + SW - 1) / SW;
+  for (int grp = blockIdx.x * warps_per_block + warp; grp < groups; grp += gridDim.x * warps_per_block)
+  {
+    const int    site0 = grp * SW + (lane % SW);
+    const bool   valid = site0 < npat;
+    const int    site = valid ? site0 : npat - 1;
+    const double w = wght[site];
+    const bool   live = valid && (w > DBL_MIN);  // lk.c:632
+    const size_t off = ((((size_t)(site >> 3) * NCATG + cat) << 3) + (site & 7)) * 4;
+    double       L[4], R[4];
+    if (left.clv)
+    {
+      const double4a v = ldg256(left.clv + off);
+      L[0] = v.x; L[1] = v.y; L[2] = v.z; L[3] = v.w;
+    }
+    else
+    {
+      const uint32_t m = tipmask[left.tip[site]];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) L[q] = (double)((m >> q) & 1u);
+    }
+    uint32_t rm = 0u;
+    if (rght.clv)
+    {
+      const double4a v = ldg256(rght.clv + off);
+      R[0] = v.x; R[1] = v.y; R[2] = v.z; R[3] = v.w;
+    }
+    else
+    {
+      rm = tipmask[rght.tip[site]];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) R[q] = (double)((rm >> q) & 1u);
+    }
+    const bool unamb = (!rght.clv) && (__popc(rm) == 1);  // lk.c:614-621
+    double     lk;
+    if (unamb)
+    {  // avx.c:119-124
+      const int st = __ffs(rm) - 1;
+      double    q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0, ps = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (k == st)
+        {
+          q0 = p[k * 4 + 0] * L[0];
+          q1 = p[k * 4 + 1] * L[1];
+          q2 = p[k * 4 + 2] * L[2];
+          q3 = p[k * 4 + 3] * L[3];
+          ps = pi[k];
+        }
+      lk = ps * hsum4(q0, q1, q2, q3);
+    }
+    else
+    {  // avx.c:125-149
+      double x[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+      {
+        double a = 0.0;
+#pragma unroll
+        for (int l = 0; l < 4; ++l) a = fma(p[k * 4 + l], L[l], a);
+        x[k] = a * (R[k] * pi[k]);
+      }
+      lk = hsum4(x[0], x[1], x[2], x[3]);
+    }
+    if (live) site_lk_cat[(size_t)site * NCATG + cat] = lk;  // lk.c:2801
+    // lk.c:816-818: site_lk = sum_c lk_c w_c in category order, on the category-0 lane
+    double term = lk * wc;
+    double site_lk = 0.0;
+#pragma unroll
+    for (int c = 0; c < NCATG; ++c) site_lk = site_lk + __shfl_sync(0xffffffffu, term, c * SW + (lane % SW));
+    if (cat == 0 && live)
+    {
+      int fact = (left.scale ? left.scale[site] : 0) + (rght.scale ? rght.scale[site] : 0);  // lk.c:2781-2791
+      if (mod->invar_flag)
+      {  // lk.c:820-842
+        bool   ovf;
+        double inv = invariant_lk(fact, invar[site], mod->pi, &ovf);
+        if (ovf)
+        {
+          fact = 0;
+          inv = invariant_lk(0, invar[site], mod->pi, &ovf);
+          site_lk = inv * mod->pinv;
+        }
+        else
+          site_lk = site_lk * (1. - mod->pinv) + inv * mod->pinv;
+      }
+      if (site_lk < DBL_MIN)
+      {  // lk.c:847-851
+        site_lk = DBL_MIN;
+        warn = 1;
+      }
+      const double lsl = log(site_lk) - kLog2 * fact;  // lk.c:854
+      site_lnl[site] = lsl;
+      site_lk_out[site] = exp(lsl);  // lk.c:857
+      fact_sum_scale[site] = fact;
+      acc[0] += w * lsl;  // lk.c:856
+    }
+  }
+  block_reduce_finish<1>(acc, warn, ro);
+}
+
+// K4, 4 states: thread per (site, category); dot_prod is [site][catg][4] (plain layout).
+template <int NCATG>
+__global__ void __launch_bounds__(128)
+    k_lnl_dlnl_dna(const double *__restrict__ dot_prod, const int *__restrict__ fact_sum_scale,
+                   const ModelDev *__restrict__ mod, double l, int with_derivative, int npat,
+                   const double *__restrict__ wght, const short *__restrict__ invar, double *__restrict__ site_lnl,
+                   ReduceOut ro)
+{
+  constexpr int SW = 32 / NCATG;
+  const int     lane = threadIdx.x & 31, cat = lane / SW;
+  const int     warps_per_block = blockDim.x >> 5, warp = threadIdx.x >> 5;
+  double        E[4], D[4];
+  {
+    double len, rr = mod->rates[cat];
+    if (with_derivative)
+    {  // lk.c:690-705
+      rr = rr * mod->br_len_mult;
+      len = l * rr;
+    }
+    else
+    {  // lk.c:596-600
+      len = fmax(0.0, l) * mod->rates[cat];
+      len = len * mod->br_len_mult;
+    }
+    if (len < mod->l_min)
+      len = mod->l_min;
+    else if (len > mod->l_max)
+      len = mod->l_max;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+      const double e = exp(mod->lambda[i] * len);
+      E[i] = e;
+      D[i] = e * mod->lambda[i] * rr;
+    }
+  }
+  const double wc = mod->probs[cat];
+  double       acc[2] = {0.0, 0.0};
+  int          warn = 0;
+  const int    groups = (npat + SW - 1) / SW;
+  for (int grp = blockIdx.x * warps_per_block + warp; grp < groups; grp += gridDim.x * warps_per_block)
+  {
+    const int    site0 = grp * SW + (lane % SW);
+    const bool   valid = site0 < npat;
+    const int    site = valid ? site0 : npat - 1;
+    const double w = wght[site];
+    const bool   live = valid && (w > DBL_MIN);
+    const double4a dp = ldg256(dot_prod + ((size_t)site * NCATG + cat) * 4);
+    double         cl, cd = 0.0;
+    if (with_derivative)
+    {  // avx.c:250-276
+      double le = fma(dp.x, E[0], 0.0), lo = fma(dp.y, E[1], 0.0);
+      double de = fma(dp.x, D[0], 0.0), dd = fma(dp.y, D[1], 0.0);
+      le = fma(dp.z, E[2], le);
+      lo = fma(dp.w, E[3], lo);
+      de = fma(dp.z, D[2], de);
+      dd = fma(dp.w, D[3], dd);
+      cl = le + lo;
+      cd = de + dd;
+    }
+    else
+    {  // avx.c:220-245
+      cl = hsum4(0.0 + dp.x * E[0], 0.0 + dp.y * E[1], 0.0 + dp.z * E[2], 0.0 + dp.w * E[3]);
+    }
+    const double tl = cl * wc, td = cd * wc;
+    double       lk = 0.0, dlk = 0.0;
+#pragma unroll
+    for (int c = 0; c < NCATG; ++c)
+    {
+      lk = lk + __shfl_sync(0xffffffffu, tl, c * SW + (lane % SW));
+      dlk = dlk + __shfl_sync(0xffffffffu, td, c * SW + (lane % SW));
+    }
+    if (cat == 0 && live)
+    {
+      int fact = fact_sum_scale[site];
+      if (mod->invar_flag)
+      {
+        bool   ovf;
+        double inv = invariant_lk(fact, invar[site], mod->pi, &ovf);
+        if (with_derivative)
+        {  // lk.c:1005-1025
+          if (ovf)
+          {
+            lk = inv * mod->pinv;
+            dlk = 0.0;
+          }
+          else
+          {
+            lk = lk * (1. - mod->pinv) + inv * mod->pinv;
+            dlk = dlk * (1. - mod->pinv);
+          }
+        }
+        else
+        {  // lk.c:910-931
+          if (ovf)
+          {
+            fact = 0;
+            inv = invariant_lk(0, invar[site], mod->pi, &ovf);
+            lk = inv * mod->pinv;
+          }
+          else
+            lk = lk * (1. - mod->pinv) + inv * mod->pinv;
+        }
+      }
+      if (lk < DBL_MIN)
+      {
+        lk = DBL_MIN;
+        warn = 1;
+      }
+      const double lsl = log(lk) - kLog2 * fact;
+      if (!with_derivative) site_lnl[site] = lsl;
+      acc[0] += w * lsl;
+      acc[1] += w * (dlk / lk);
+    }
+  }
+  block_reduce_finish<2>(acc, warn, ro);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K3: thread per (site, category).
 __global__ void __launch_bounds__(128)
     k_eigen_lr(SideDev left, SideDev rght, const ModelDev *__restrict__ mod, int npat, int ns, int ncatg,
