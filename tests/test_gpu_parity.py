@@ -197,6 +197,17 @@ def test_many_updates_multi_chunk():
         assert abs(gpu.Lk(e) - cpu.Lk(e)) <= 1e-12 * abs(cpu.c_lnL)
 
 
+def test_tensor_pipe_dna_variant_is_bit_identical(monkeypatch):
+    """The opt-in tensor-pipe variant of the 4-state kernel (PLK_DNA_MMA=1, one DMMA.8x8x4 per 8 sites,
+    category and child) must reproduce the reference bit for bit as well (DMMA = ascending-k FMA chain)."""
+    monkeypatch.setenv("PLK_DNA_MMA", "1")
+    for case in ("nucleic_hky", "synth_dna_deep"):
+        c, eng = make(case)
+        pc.check_full_traversal(c, eng, clv_rtol=0, exact=True)
+        c, eng = make(case)
+        pc.check_lnl_end_to_end(c, eng, rtol=1e-12)
+
+
 def test_error_paths():
     from phyml_b200.engine import EngineError
     from phyml_b200.tree import Side
