@@ -60,6 +60,9 @@ typedef struct
   int           map_cap, n_clv, n_pm, clv_cap, pm_cap;
   plk_op       *queue;
   int           n_queue, queue_cap;
+  int           pm_h[64];  /* deferred P-matrix updates: handle, branch length */
+  double        pm_l[64];
+  int           n_pm_queue;
   double        model_print[8 + 2 * 32 + 2 * 16]; /* fingerprint of the uploaded model */
   int           model_valid;
   long long     n_lk, n_dlk, n_partial, n_flush, n_pmat;
@@ -129,6 +132,11 @@ static void upload_model_if_changed(shim_t *sh)
   fp[5] = mod->eigen->r_e_vect[1];
   fp[6] = mod->eigen->l_e_vect[ns > 1 ? ns : 0];
   if (sh->model_valid && !memcmp(fp, sh->model_print, sizeof(fp))) return;
+  if (sh->n_pm_queue > 0)
+  { /* P-matrices queued under the previous parameter values are computed with them, as the reference did */
+    CK(plk_update_pmats(sh->inst, sh->n_pm_queue, sh->pm_h, sh->pm_l), sh);
+    sh->n_pm_queue = 0;
+  }
   CK(plk_set_model(sh->inst, mod->eigen->r_e_vect, mod->eigen->l_e_vect, mod->eigen->e_val, mod->e_frq->pi->v,
                    mod->ras->gamma_rr->v, mod->ras->gamma_r_proba->v, mod->ras->pinvar->v, mod->ras->invar,
                    mod->l_min, mod->l_max, mod->br_len_mult->v),
@@ -137,8 +145,16 @@ static void upload_model_if_changed(shim_t *sh)
   sh->model_valid = 1;
 }
 
+/* Deferred work is executed as: all queued P-matrix updates in ONE batched launch, then all queued CLV
+   updates in ONE fused launch.  That order is valid because a P-matrix update is only queued when no
+   CLV update queued before it reads that matrix (otherwise everything is flushed first). */
 static void flush(shim_t *sh)
 {
+  if (sh->n_pm_queue > 0)
+  {
+    CK(plk_update_pmats(sh->inst, sh->n_pm_queue, sh->pm_h, sh->pm_l), sh);
+    sh->n_pm_queue = 0;
+  }
   if (sh->n_queue == 0) return;
   CK(plk_update_partials(sh->inst, sh->n_queue, sh->queue), sh);
   sh->n_queue = 0;
@@ -268,14 +284,19 @@ void Update_PMat_At_Given_Edge(t_edge *b_fcus, t_tree *tree)
     return;
   }
   assert(b_fcus && b_fcus->Pij_rr);
-  /* queued CLV updates must see the P-matrices as they were when Update_Partial_Lk was called */
-  flush(sh);
   h = pm_handle(sh, b_fcus->Pij_rr);
   sh->n_pmat++;
+  { /* a queued CLV update must see this matrix as it was when Update_Partial_Lk was called */
+    int i, conflict = 0;
+    for (i = 0; i < sh->n_queue; ++i)
+      if (sh->queue[i].pmat1 == h || sh->queue[i].pmat2 == h) conflict = 1;
+    if (conflict || sh->n_pm_queue == 64) flush(sh);
+  }
   if (b_fcus->has_zero_br_len == YES)
   { /* identity matrices (PMat_Zero_Br_Len, models.c:331): host-computed, uploaded */
     int     ns = tree->mod->ns, nc = tree->mod->ras->n_catg, c, i;
     double *P = (double *)calloc((size_t)nc * ns * ns, sizeof(double));
+    flush(sh);
     for (c = 0; c < nc; ++c)
       for (i = 0; i < ns; ++i) P[(size_t)c * ns * ns + i * ns + i] = 1.0;
     CK(plk_set_pmat(sh->inst, h, P), sh);
@@ -284,7 +305,18 @@ void Update_PMat_At_Given_Edge(t_edge *b_fcus, t_tree *tree)
   }
   upload_model_if_changed(sh);
   l = (tree->mod->log_l == YES) ? exp(b_fcus->l->v) : b_fcus->l->v; /* lk.c:2278 */
-  CK(plk_update_pmats(sh->inst, 1, &h, &l), sh);
+  { /* defer: the latest length of a handle wins */
+    int i;
+    for (i = 0; i < sh->n_pm_queue; ++i)
+      if (sh->pm_h[i] == h)
+      {
+        sh->pm_l[i] = l;
+        return;
+      }
+    sh->pm_h[sh->n_pm_queue] = h;
+    sh->pm_l[sh->n_pm_queue] = l;
+    sh->n_pm_queue++;
+  }
 }
 
 /* ------------------------------------------------------------------------------------------------ */
