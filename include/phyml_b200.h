@@ -52,7 +52,7 @@ typedef struct plk_config
 {
   int n_tips;     /* n_otu */
   int n_patterns; /* data->n_pattern owned by THIS instance (its shard when site-sharded) */
-  int ns;         /* mod->ns: 4 and 20 have specialised kernels, 2..64 run the generic kernel */
+  int ns;         /* mod->ns: 4 and 20 have specialised fused kernels, other 2..32 run the generic kernel */
   int ncatg;      /* mod->ras->n_catg (1..16) */
   int n_clv;      /* number of CLV handles (2 per edge: p_lk_left, p_lk_rght); storage is lazy */
   int n_pmat;     /* number of P-matrix handles (1 per edge: Pij_rr) */
