@@ -169,6 +169,18 @@ int plk_comm_p2p_init(plk_instance *inst, int rank, int world, const void *handl
 /* after plk_comm_init, plk_edge_lnl / _dlnl / _eigen return the ALL-RANK sum when enabled */
 int plk_comm_set_allreduce(plk_instance *inst, int enable);
 
+/* ---- site sharding across GPUs inside ONE process (the reference is one process, one t_tree) -----
+ * SURVEY.md section 8(e) "one process, 8 devices": cfg->n_patterns is the whole alignment
+ * (cfg->device is ignored); device devices[i] (NULL: 0..n_gpus-1) owns the i-th contiguous block of
+ * patterns of every per-site buffer, P-matrices and the model are replicated.  The returned instance
+ * takes every call of this header with whole-alignment arrays; scalar results are the all-shard
+ * sums (the partial sums are exchanged inside the reduction kernels over NVLink peer memory when
+ * the devices can map each other, else added on the host in shard order).  This is what lets
+ * lk.c's single t_tree (src/lk.c:443, src/make.c:17) drive all GPUs of a box.
+ * The same device may be listed several times (shards then share it; used by the 1-GPU tests). */
+int plk_create_sharded(const plk_config *cfg, int n_gpus, const int *devices, plk_instance **out);
+int plk_n_shards(const plk_instance *inst);
+
 /* ---- introspection ---------------------------------------------------------------------------- */
 /* kernels launched so far by this instance (bench.py's gpu_launches) */
 long long plk_launch_count(const plk_instance *inst);

@@ -14,7 +14,11 @@
  *   --time N    : times N calls of Lk(NULL,tree) (both_sides as given) and prints one JSON line
  *                 (the "reference" CPU baseline of bench.py).
  *
- * usage: ref_driver [--dump FILE] [--time N] [--warmup W] [--both_sides 0|1] [--dlk N_EDGES] -- <phyml args>
+ *   --summary FILE : after Lk(NULL) writes only the small things a full-size parity pin needs (sizes, the
+ *                 model's eigen system and rates, lnL, pattern weights, per-pattern lnL) -- used by
+ *                 tests/golden/make_golden_big.py for the BASELINE.json configurations.
+ *
+ * usage: ref_driver [--dump FILE] [--summary FILE] [--time N] [--warmup W] [--both_sides 0|1] [--dlk N_EDGES] -- <phyml args>
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -205,9 +209,37 @@ static void dump_all(t_tree *tree, int n_dlk_edges)
   }
 }
 
+static void dump_summary(t_tree *tree)
+{
+  const int P = tree->data->n_pattern;
+  const int ns = tree->mod->ns;
+  const int ncatg = tree->mod->ras->n_catg;
+  rec_1i("n_otu", tree->n_otu);
+  rec_1i("n_pattern", P);
+  rec_1i("ns", ns);
+  rec_1i("ncatg", ncatg);
+  rec_1i("invar_flag", tree->mod->ras->invar);
+  rec_1d("pinvar", tree->mod->ras->pinvar->v);
+  rec_1d("l_min", tree->mod->l_min);
+  rec_1d("l_max", tree->mod->l_max);
+  rec_1d("br_len_mult", tree->mod->br_len_mult->v);
+  rec_1d("alpha", tree->mod->ras->alpha->v);
+  rec_d("U", ns * ns, tree->mod->eigen->r_e_vect);
+  rec_d("V", ns * ns, tree->mod->eigen->l_e_vect);
+  rec_d("lambda", ns, tree->mod->eigen->e_val);
+  rec_d("pi", ns, tree->mod->e_frq->pi->v);
+  rec_d("rates", ncatg, tree->mod->ras->gamma_rr->v);
+  rec_d("rate_probs", ncatg, tree->mod->ras->gamma_r_proba->v);
+  rec_1d("lnL", tree->c_lnL);
+  rec_d("wght", P, tree->data->wght);
+  rec_h("invar", P, tree->data->invar);
+  rec_d("site_lnl", P, tree->c_lnL_sorted);
+  rec_i("fact_sum_scale", P, tree->fact_sum_scale);
+}
+
 int main(int argc, char **argv)
 {
-  const char *dump_file = NULL;
+  const char *dump_file = NULL, *summary_file = NULL;
   int n_time = 0, n_warm = 0, both_sides = 0, n_dlk = 4;
   int i, split = -1;
   option *io;
@@ -224,6 +256,8 @@ int main(int argc, char **argv)
     }
     else if (!strcmp(argv[i], "--dump") && i + 1 < argc)
       dump_file = argv[++i];
+    else if (!strcmp(argv[i], "--summary") && i + 1 < argc)
+      summary_file = argv[++i];
     else if (!strcmp(argv[i], "--time") && i + 1 < argc)
       n_time = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--warmup") && i + 1 < argc)
@@ -301,6 +335,19 @@ int main(int argc, char **argv)
            tree->n_otu, tree->data->n_pattern, tree->mod->ns, tree->mod->ras->n_catg, both_sides, n_time,
            tot / n_time, best, tree->c_lnL);
     free(t);
+  }
+
+  if (summary_file)
+  {
+    g_out = fopen(summary_file, "wb");
+    if (!g_out)
+    {
+      perror(summary_file);
+      return 1;
+    }
+    dump_summary(tree);
+    fclose(g_out);
+    g_out = NULL;
   }
 
   if (dump_file)

@@ -63,6 +63,7 @@ NcclApi g_nccl;
 constexpr int    kStageSlots = 8;
 constexpr size_t kStageBytes = 256 * 1024;
 constexpr int    kMaxReduceBlocks = 4096;
+constexpr size_t kSitePad = 32;  // per-site arrays are padded so that the last 32-item chunk can be read unpredicated
 }  // namespace
 
 struct plk_instance
@@ -99,6 +100,7 @@ struct plk_instance
   ResultHost        *h_result = nullptr;
   ResultHost        *h_result_dev = nullptr;
   unsigned long long seq = 0;
+  unsigned long long coll_seq = 0;  // cross-GPU exchange counter: reset whenever the mailboxes are (re)wired
 
   // pinned staging ring for small descriptor uploads
   char       *h_stage[kStageSlots] = {};
@@ -126,11 +128,19 @@ struct plk_instance
   double l_min = 1e-8, l_max = 100.0;  // host copy of mod->l_min / l_max (plk_set_model)
   int    trav_umax = 2;                // items per thread of the fused traversal kernel
   int    trav_blocks_per_sm = 2;
+  int    trav_v1 = 0;            // PLK_TRAV_V1=1: first-generation kernel (k_traverse_dna), kept for A/B measurements
+  int    t2_variant = 0;         // PLK_T2_VARIANT: (compute warps, blocks/SM) of k_traverse_dna2
   bool   aa_attr_set = false;
   int    blocked = 0;            // CLVs in the blocked layout (ns = 4, 20), see clv_off()
   int    dna_mma = 0;            // use k_traverse_dna_mma (tensor-pipe variant) for ns = 4
   int    mma_u = 2;
   double *d_tmp_clv = nullptr;   // plain-layout staging for plk_get_clv / plk_set_clv
+
+  // single-process site sharding (plk_create_sharded): this object is then only a dispatcher over one
+  // ordinary instance per device, each owning the contiguous pattern block [shard_lo[i], shard_lo[i+1])
+  std::vector<plk_instance *> shards;
+  std::vector<int>            shard_lo;
+  bool                        inproc_p2p = false;
 
   // scheduling scratch
   std::vector<int> lvl_write, lvl_read, op_level;
@@ -165,6 +175,40 @@ struct plk_instance
 
 namespace
 {
+bool g_multi_device = false;  // set once a sharded instance exists: every entry point then selects its device
+
+inline int use_device(plk_instance *inst)
+{
+  if (g_multi_device) CU_TRY(inst, cudaSetDevice(inst->cfg.device));
+  return PLK_OK;
+}
+#define USE_DEVICE(inst)          \
+  do                              \
+  {                               \
+    int rc_ = use_device(inst);   \
+    if (rc_) return rc_;          \
+  } while (0)
+
+// run `call` (an expression using `sh`, the shard, and `lo`/`n`, its pattern block) on every shard
+#define FOR_SHARDS(inst, call)                                                   \
+  do                                                                             \
+  {                                                                              \
+    for (size_t i_ = 0; i_ < (inst)->shards.size(); ++i_)                        \
+    {                                                                            \
+      plk_instance *sh = (inst)->shards[i_];                                     \
+      const size_t  lo = (size_t)(inst)->shard_lo[i_];                           \
+      const size_t  n = (size_t)((inst)->shard_lo[i_ + 1] - (inst)->shard_lo[i_]); \
+      (void)lo;                                                                  \
+      (void)n;                                                                   \
+      int rc_ = (call);                                                          \
+      if (rc_)                                                                   \
+      {                                                                          \
+        (inst)->err = "shard " + std::to_string(i_) + ": " + sh->err;            \
+        return rc_;                                                              \
+      }                                                                          \
+    }                                                                            \
+  } while (0)
+
 template <typename T>
 int dev_alloc(plk_instance *inst, T **p, size_t n)
 {
@@ -181,7 +225,8 @@ size_t clv_elems_plain(const plk_instance *inst)
 }
 size_t clv_elems(const plk_instance *inst)
 {
-  const size_t sites = inst->blocked ? (((size_t)inst->cfg.n_patterns + 7) & ~(size_t)7) : (size_t)inst->cfg.n_patterns;
+  // blocked layout: whole 32-site chunks (a warp of the fused kernels may read up to 31 sites past the last pattern)
+  const size_t sites = inst->blocked ? (((size_t)inst->cfg.n_patterns + 31) & ~(size_t)31) : (size_t)inst->cfg.n_patterns;
   return sites * inst->cfg.ncatg * inst->cfg.ns;
 }
 
@@ -191,11 +236,11 @@ int ensure_clv(plk_instance *inst, int h)
   int rc = dev_alloc(inst, &inst->clv[h], clv_elems(inst) + 4);
   if (rc) return rc;
   inst->alloc_epoch++;
-  rc = dev_alloc(inst, &inst->scale[h], (size_t)inst->cfg.n_patterns);
+  rc = dev_alloc(inst, &inst->scale[h], (size_t)inst->cfg.n_patterns + kSitePad);
   if (rc) return rc;
   // zero-weight patterns are never written by K1 (avx.c:515-520): start from defined contents
   CU_TRY(inst, cudaMemsetAsync(inst->clv[h], 0, clv_elems(inst) * sizeof(double), inst->stream));
-  CU_TRY(inst, cudaMemsetAsync(inst->scale[h], 0, (size_t)inst->cfg.n_patterns * sizeof(int), inst->stream));
+  CU_TRY(inst, cudaMemsetAsync(inst->scale[h], 0, ((size_t)inst->cfg.n_patterns + kSitePad) * sizeof(int), inst->stream));
   return PLK_OK;
 }
 
@@ -266,6 +311,7 @@ ReduceOut make_reduce_out(plk_instance *inst)
   ro.dev_out = inst->d_result;
   ro.host_out = inst->h_result_dev;
   ro.seq = ++inst->seq;
+  ro.coll_seq = inst->p2p ? ++inst->coll_seq : 0;
   ro.publish = inst->allreduce ? 0 : 1;
   ro.peers = inst->p2p ? inst->d_peers : nullptr;
   ro.rank = inst->rank;
@@ -276,6 +322,7 @@ ReduceOut make_reduce_out(plk_instance *inst)
 // finish a reduction: optional all-reduce + publish, then wait for the mapped result
 int finish_reduction(plk_instance *inst, double *out0, double *out1, int *warn)
 {
+  USE_DEVICE(inst);
   const unsigned long long seq = inst->seq;
   if (inst->allreduce)
   {
@@ -313,9 +360,14 @@ int finish_reduction(plk_instance *inst, double *out0, double *out1, int *warn)
       if (q != cudaErrorNotReady) CU_TRY(inst, q);
     }
   }
+  if (h->warn & kWarnPeerTimeout)
+  {
+    inst->err = "cross-GPU exchange timed out: a peer rank did not post its partial sum";
+    return PLK_ERR_STATE;
+  }
   if (out0) *out0 = h->val[0];
   if (out1) *out1 = h->val[1];
-  if (warn) *warn = h->warn;
+  if (warn) *warn = h->warn & 1;
   return PLK_OK;
 }
 }  // namespace
@@ -390,6 +442,8 @@ int plk_create(const plk_config *cfg, plk_instance **out)
   inst->num_sms = prop.multiProcessorCount;
   if (const char *e = getenv("PLK_TRAV_UMAX")) inst->trav_umax = (atoi(e) == 1) ? 1 : 2;
   if (const char *e = getenv("PLK_DNA_MMA")) inst->dna_mma = atoi(e) != 0;
+  if (const char *e = getenv("PLK_TRAV_V1")) inst->trav_v1 = atoi(e) != 0;
+  if (const char *e = getenv("PLK_T2_VARIANT")) inst->t2_variant = atoi(e);
   if (const char *e = getenv("PLK_TRAV_BLOCKS_PER_SM")) inst->trav_blocks_per_sm = std::max(1, std::min(4, atoi(e)));
   CREATE_TRY(cudaStreamCreateWithFlags(&inst->stream, cudaStreamNonBlocking));
 
@@ -401,11 +455,15 @@ int plk_create(const plk_config *cfg, plk_instance **out)
   inst->clv.assign(cfg->n_clv, nullptr);
   inst->scale.assign(cfg->n_clv, nullptr);
 
-  CREATE_RC(dev_alloc(inst, &inst->d_wght, P));
+  CREATE_RC(dev_alloc(inst, &inst->d_wght, P + kSitePad));  // padding keeps weight 0: never stored by K1
   CREATE_RC(dev_alloc(inst, &inst->d_invar, P));
   CREATE_RC(dev_alloc(inst, &inst->d_tipmask, 256));
-  CREATE_RC(dev_alloc(inst, &inst->d_tipcodes, inst->tip_stride * cfg->n_tips));
-  if (cfg->ns == 4 || cfg->ns == 20) CREATE_RC(dev_alloc(inst, &inst->d_tiprows, inst->tip_stride * cfg->n_tips));
+  CREATE_RC(dev_alloc(inst, &inst->d_tipcodes, inst->tip_stride * cfg->n_tips + kSitePad));
+  if (cfg->ns == 4 || cfg->ns == 20)
+  {
+    CREATE_RC(dev_alloc(inst, &inst->d_tiprows, inst->tip_stride * cfg->n_tips + kSitePad));
+    CREATE_TRY(cudaMemsetAsync(inst->d_tiprows, 0, inst->tip_stride * cfg->n_tips + kSitePad, inst->stream));
+  }
   CREATE_RC(dev_alloc(inst, &inst->d_model, 1));
   CREATE_RC(dev_alloc(inst, &inst->d_pmat, inst->pmat_stride * cfg->n_pmat));
   CREATE_RC(dev_alloc(inst, &inst->d_site_lnl, P));
@@ -417,10 +475,10 @@ int plk_create(const plk_config *cfg, plk_instance **out)
   CREATE_RC(dev_alloc(inst, &inst->d_ticket, 1));
   CREATE_RC(dev_alloc(inst, &inst->d_result, 4));
   CREATE_RC(dev_alloc(inst, &inst->d_stage, (size_t)kStageSlots * kStageBytes));
-  CREATE_TRY(cudaMemsetAsync(inst->d_wght, 0, P * sizeof(double), inst->stream));
+  CREATE_TRY(cudaMemsetAsync(inst->d_wght, 0, (P + kSitePad) * sizeof(double), inst->stream));
   CREATE_TRY(cudaMemsetAsync(inst->d_invar, 0xff, P * sizeof(short), inst->stream));
   CREATE_TRY(cudaMemsetAsync(inst->d_tipmask, 0, 256 * sizeof(uint32_t), inst->stream));
-  CREATE_TRY(cudaMemsetAsync(inst->d_tipcodes, 0, inst->tip_stride * cfg->n_tips, inst->stream));
+  CREATE_TRY(cudaMemsetAsync(inst->d_tipcodes, 0, inst->tip_stride * cfg->n_tips + kSitePad, inst->stream));
   CREATE_TRY(cudaMemsetAsync(inst->d_warn, 0, sizeof(int), inst->stream));
   CREATE_TRY(cudaMemsetAsync(inst->d_ticket, 0, sizeof(unsigned int), inst->stream));
   CREATE_TRY(cudaMemsetAsync(inst->d_pmat, 0, inst->pmat_stride * cfg->n_pmat * sizeof(double), inst->stream));
@@ -444,6 +502,12 @@ int plk_create(const plk_config *cfg, plk_instance **out)
 void plk_destroy(plk_instance *inst)
 {
   if (!inst) return;
+  if (!inst->shards.empty())
+  {
+    for (plk_instance *sh : inst->shards) plk_destroy(sh);
+    delete inst;
+    return;
+  }
   cudaSetDevice(inst->cfg.device);
   if (inst->stream) cudaStreamSynchronize(inst->stream);
   if (inst->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(inst->comm);
@@ -483,6 +547,12 @@ void plk_destroy(plk_instance *inst)
 
 int plk_sync(plk_instance *inst)
 {
+  if (!inst->shards.empty())
+  {
+    FOR_SHARDS(inst, plk_sync(sh));
+    return PLK_OK;
+  }
+  USE_DEVICE(inst);
   CU_TRY(inst, cudaStreamSynchronize(inst->stream));
   return PLK_OK;
 }
@@ -491,6 +561,12 @@ int plk_sync(plk_instance *inst)
 int plk_set_pattern_weights(plk_instance *inst, const double *wght, const short *invar)
 {
   ARG_CHECK(inst, wght != nullptr, "wght is NULL");
+  if (!inst->shards.empty())
+  {
+    FOR_SHARDS(inst, plk_set_pattern_weights(sh, wght + lo, invar ? invar + lo : nullptr));
+    return PLK_OK;
+  }
+  USE_DEVICE(inst);
   const size_t P = inst->cfg.n_patterns;
   CU_TRY(inst, cudaMemcpyAsync(inst->d_wght, wght, P * sizeof(double), cudaMemcpyHostToDevice, inst->stream));
   if (invar)
@@ -514,6 +590,12 @@ static int upload_masks(plk_instance *inst)
 int plk_set_tip_table(plk_instance *inst, int n_codes, const double *vectors)
 {
   ARG_CHECK(inst, n_codes >= 1 && n_codes <= 256 && vectors, "tip table: 1..256 codes");
+  if (!inst->shards.empty())
+  {
+    FOR_SHARDS(inst, plk_set_tip_table(sh, n_codes, vectors));
+    return PLK_OK;
+  }
+  USE_DEVICE(inst);
   const int ns = inst->cfg.ns;
   inst->tip_table.assign(vectors, vectors + (size_t)n_codes * ns);
   inst->masks.assign(n_codes, 0u);
@@ -532,6 +614,12 @@ int plk_set_tip_table(plk_instance *inst, int n_codes, const double *vectors)
 int plk_set_tip_codes(plk_instance *inst, int tip, const uint8_t *codes)
 {
   ARG_CHECK(inst, tip >= 0 && tip < inst->cfg.n_tips && codes, "tip index out of range");
+  if (!inst->shards.empty())
+  {
+    FOR_SHARDS(inst, plk_set_tip_codes(sh, tip, codes + lo));
+    return PLK_OK;
+  }
+  USE_DEVICE(inst);
   CU_TRY(inst, cudaMemcpyAsync(inst->d_tipcodes + (size_t)tip * inst->tip_stride, codes, inst->cfg.n_patterns,
                                cudaMemcpyHostToDevice, inst->stream));
   inst->tiprows_dirty = true;
@@ -541,6 +629,12 @@ int plk_set_tip_codes(plk_instance *inst, int tip, const uint8_t *codes)
 int plk_set_all_tip_codes(plk_instance *inst, const uint8_t *codes, size_t host_stride)
 {
   ARG_CHECK(inst, codes && host_stride >= (size_t)inst->cfg.n_patterns, "plk_set_all_tip_codes: bad arguments");
+  if (!inst->shards.empty())
+  {
+    FOR_SHARDS(inst, plk_set_all_tip_codes(sh, codes + lo, host_stride));
+    return PLK_OK;
+  }
+  USE_DEVICE(inst);
   if (host_stride == inst->tip_stride)
     CU_TRY(inst, cudaMemcpyAsync(inst->d_tipcodes, codes, inst->tip_stride * inst->cfg.n_tips, cudaMemcpyHostToDevice,
                                  inst->stream));
@@ -554,6 +648,12 @@ int plk_set_all_tip_codes(plk_instance *inst, const uint8_t *codes, size_t host_
 int plk_set_tip_vectors(plk_instance *inst, int tip, const double *v)
 {
   ARG_CHECK(inst, tip >= 0 && tip < inst->cfg.n_tips && v, "tip index out of range");
+  if (!inst->shards.empty())
+  {
+    FOR_SHARDS(inst, plk_set_tip_vectors(sh, tip, v + lo * (size_t)inst->cfg.ns));
+    return PLK_OK;
+  }
+  USE_DEVICE(inst);
   const int            ns = inst->cfg.ns, P = inst->cfg.n_patterns;
   std::vector<uint8_t> codes(P);
   bool                 table_grew = false;
@@ -593,6 +693,14 @@ int plk_set_model(plk_instance *inst, const double *U, const double *V, const do
                   double l_max, double br_len_mult)
 {
   ARG_CHECK(inst, U && V && lambda && pi && rates && rate_probs, "plk_set_model: NULL array");
+  if (!inst->shards.empty())
+  {
+    FOR_SHARDS(inst, plk_set_model(sh, U, V, lambda, pi, rates, rate_probs, pinv, invar_flag, l_min, l_max, br_len_mult));
+    inst->l_min = l_min;
+    inst->l_max = l_max;
+    return PLK_OK;
+  }
+  USE_DEVICE(inst);
   const int ns = inst->cfg.ns, nc = inst->cfg.ncatg;
   ModelDev *m = new ModelDev();
   memset(m, 0, sizeof(ModelDev));
@@ -622,6 +730,12 @@ int plk_set_model(plk_instance *inst, const double *U, const double *V, const do
 int plk_update_pmats(plk_instance *inst, int n, const int *pmat, const double *l)
 {
   ARG_CHECK(inst, n >= 0 && (n == 0 || (pmat && l)), "plk_update_pmats: bad arguments");
+  if (!inst->shards.empty())
+  {  // P-matrices are replicated (bytes): every shard computes its own copy
+    FOR_SHARDS(inst, plk_update_pmats(sh, n, pmat, l));
+    return PLK_OK;
+  }
+  USE_DEVICE(inst);
   const int    ns = inst->cfg.ns, nc = inst->cfg.ncatg;
   const int    per_slot = (int)(kStageBytes / sizeof(PmatJob));
   const int    threads = ((ns * ns + 31) / 32) * 32;
@@ -650,6 +764,12 @@ int plk_update_pmats(plk_instance *inst, int n, const int *pmat, const double *l
 int plk_set_pmat(plk_instance *inst, int pmat, const double *P)
 {
   ARG_CHECK(inst, pmat >= 0 && pmat < inst->cfg.n_pmat && P, "pmat handle out of range");
+  if (!inst->shards.empty())
+  {
+    FOR_SHARDS(inst, plk_set_pmat(sh, pmat, P));
+    return PLK_OK;
+  }
+  USE_DEVICE(inst);
   std::vector<double> rec(inst->pmat_stride);
   memcpy(rec.data(), P, inst->pmat_elems * sizeof(double));
   if (inst->cfg.ns == 4)
@@ -707,6 +827,8 @@ int plk_set_pmat(plk_instance *inst, int pmat, const double *P)
 int plk_get_pmat(plk_instance *inst, int pmat, double *P)
 {
   ARG_CHECK(inst, pmat >= 0 && pmat < inst->cfg.n_pmat && P, "pmat handle out of range");
+  if (!inst->shards.empty()) return plk_get_pmat(inst->shards[0], pmat, P);
+  USE_DEVICE(inst);
   CU_TRY(inst, cudaMemcpyAsync(P, inst->d_pmat + (size_t)pmat * inst->pmat_stride, inst->pmat_elems * sizeof(double),
                                cudaMemcpyDeviceToHost, inst->stream));
   CU_TRY(inst, cudaStreamSynchronize(inst->stream));
@@ -843,12 +965,79 @@ static int launch_traverse(plk_instance *inst, const OpDev *d_ops, int n_ops)
   return PLK_ERR_ARG;
 }
 
+// op-major 4-state traversal (k_traverse_dna2): one tile of 32-item chunks per block and launch
+template <int NCATG, int W, int MINB>
+static int launch_traverse2_t(plk_instance *inst, const OpDev *d_ops, int n_ops)
+{
+  constexpr int    SW = 32 / NCATG;
+  constexpr size_t kSmemPerSm = 227 * 1024;
+  const int        total_chunks = (inst->cfg.n_patterns + SW - 1) / SW;
+  const size_t     budget = kSmemPerSm / MINB - 2048;
+  int              cap = (int)((budget - t2_smem_bytes<NCATG>(0)) / kT2ChunkBytes);
+  cap = std::min(cap, 32 * W) & ~1;  // live mask is 32 bits per warp; even: tiles start on 8-site blocks for NCATG = 8
+  const int       slots = inst->num_sms * MINB;
+  const long long per_round = (long long)slots * cap;
+  const int       rounds = (int)((total_chunks + per_round - 1) / per_round);
+  int             n_tiles = std::max(1, std::min(slots * rounds, total_chunks));
+  int             tile_chunks = (total_chunks + n_tiles - 1) / n_tiles;
+  tile_chunks = std::min((tile_chunks + 1) & ~1, cap);
+  n_tiles = (total_chunks + tile_chunks - 1) / tile_chunks;
+  const int    grid = std::min(n_tiles, slots);
+  const size_t smem = t2_smem_bytes<NCATG>(tile_chunks);
+  auto         kern = k_traverse_dna2<NCATG, W, MINB>;
+  static size_t smem_set = 0;  // per instantiation
+  if (smem > smem_set)
+  {
+    CU_TRY(inst, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(budget)));
+    smem_set = budget;
+  }
+  kern<<<grid, (W + 1) * 32, smem, inst->stream>>>(d_ops, n_ops, total_chunks, tile_chunks, n_tiles, inst->d_wght,
+                                                    inst->apply_scaling);
+  inst->launches++;
+  CU_TRY(inst, cudaGetLastError());
+  return PLK_OK;
+}
+
+template <int NCATG>
+static int launch_traverse2_nc(plk_instance *inst, const OpDev *d_ops, int n_ops)
+{
+  constexpr int kW1 = (NCATG == 8) ? 10 : 11;  // 8 categories: a chunk is half an 8-site block, W must be even
+  switch (inst->t2_variant)
+  {
+  case 1: return launch_traverse2_t<NCATG, 6, 2>(inst, d_ops, n_ops);
+  case 2: return launch_traverse2_t<NCATG, 12, 1>(inst, d_ops, n_ops);
+  case 3: return launch_traverse2_t<NCATG, 10, 1>(inst, d_ops, n_ops);
+  case 4: return launch_traverse2_t<NCATG, 14, 1>(inst, d_ops, n_ops);
+  case 5: return launch_traverse2_t<NCATG, (NCATG == 8) ? 4 : 5, 2>(inst, d_ops, n_ops);
+  default: return launch_traverse2_t<NCATG, kW1, 1>(inst, d_ops, n_ops);
+  }
+}
+
+static int launch_traverse2(plk_instance *inst, const OpDev *d_ops, int n_ops)
+{
+  switch (inst->cfg.ncatg)
+  {
+  case 1: return launch_traverse2_nc<1>(inst, d_ops, n_ops);
+  case 2: return launch_traverse2_nc<2>(inst, d_ops, n_ops);
+  case 4: return launch_traverse2_nc<4>(inst, d_ops, n_ops);
+  case 8: return launch_traverse2_nc<8>(inst, d_ops, n_ops);
+  }
+  inst->err = "internal: unsupported ncatg for traversal kernel";
+  return PLK_ERR_ARG;
+}
+
 extern "C" {
 
 int plk_update_partials(plk_instance *inst, int n_ops, const plk_op *ops)
 {
   ARG_CHECK(inst, n_ops >= 0 && (n_ops == 0 || ops), "plk_update_partials: bad arguments");
   if (n_ops == 0) return PLK_OK;
+  if (!inst->shards.empty())
+  {  // asynchronous on every device's stream: the shards run concurrently
+    FOR_SHARDS(inst, plk_update_partials(sh, n_ops, ops));
+    return PLK_OK;
+  }
+  USE_DEVICE(inst);
   const int  nclv = inst->cfg.n_clv;
   const int  nc = inst->cfg.ncatg;
   const bool fused_dna = inst->fused_dna, fused_aa = inst->fused_aa;
@@ -869,7 +1058,8 @@ int plk_update_partials(plk_instance *inst, int n_ops, const plk_op *ops)
   const int per_slot = (int)(kStageBytes / sizeof(OpDev));
   auto launch_fused = [&](const OpDev *d_ops, int n) {
     return (fused_dna && inst->dna_mma && nc <= 4) ? launch_traverse_mma(inst, d_ops, n)
-           : fused_dna                             ? launch_traverse(inst, d_ops, n)
+           : (fused_dna && inst->trav_v1)          ? launch_traverse(inst, d_ops, n)
+           : fused_dna                             ? launch_traverse2(inst, d_ops, n)
                                                    : launch_traverse_aa(inst, d_ops, n);
   };
   if (fused && inst->d_ops_cache && inst->cache_epoch == inst->alloc_epoch && (int)inst->cache_ops.size() == n_ops &&
@@ -1021,13 +1211,47 @@ int plk_update_partials(plk_instance *inst, int n_ops, const plk_op *ops)
 }
 
 // ---- K2 ------------------------------------------------------------------------------------------
-int plk_edge_lnl(plk_instance *inst, plk_side left, plk_side rght, int pmat, double *lnl, int *warn)
+// sum of the shards' partial results in shard order (or, with the in-process P2P exchange, the all-shard sum
+// that every shard's reduction kernel computed itself)
+static int finish_sharded(plk_instance *inst, double *out0, double *out1, int *warn)
 {
+  double t0 = 0.0, t1 = 0.0;
+  int    w = 0;
+  for (size_t i = 0; i < inst->shards.size(); ++i)
+  {
+    double a = 0.0, b = 0.0;
+    int    ww = 0;
+    const int rc = finish_reduction(inst->shards[i], &a, &b, &ww);
+    if (rc)
+    {
+      inst->err = "shard " + std::to_string(i) + ": " + inst->shards[i]->err;
+      return rc;
+    }
+    if (inst->inproc_p2p)
+    {
+      if (i == 0) t0 = a, t1 = b, w = ww;
+    }
+    else
+    {
+      t0 += a;
+      t1 += b;
+      w |= ww;
+    }
+  }
+  if (out0) *out0 = t0;
+  if (out1) *out1 = t1;
+  if (warn) *warn = w;
+  return PLK_OK;
+}
+
+static int edge_lnl_launch(plk_instance *inst, plk_side left, plk_side rght, int pmat)
+{
+  USE_DEVICE(inst);
   int rc = check_side(inst, left, true);
   if (rc) return rc;
   rc = check_side(inst, rght, true);
   if (rc) return rc;
-  ARG_CHECK(inst, pmat >= 0 && pmat < inst->cfg.n_pmat && lnl, "plk_edge_lnl: bad arguments");
+  ARG_CHECK(inst, pmat >= 0 && pmat < inst->cfg.n_pmat, "plk_edge_lnl: bad arguments");
   if (inst->fused_dna && inst->cfg.ncatg == 4)
   {  // coalesced 4-state kernel on the blocked layout: thread per (site, category)
     const int groups = (inst->cfg.n_patterns + 7) / 8;
@@ -1050,12 +1274,31 @@ int plk_edge_lnl(plk_instance *inst, plk_side left, plk_side rght, int pmat, dou
   inst->launches++;
   CU_TRY(inst, cudaGetLastError());
   inst->site_valid = true;
+  return PLK_OK;
+}
+
+int plk_edge_lnl(plk_instance *inst, plk_side left, plk_side rght, int pmat, double *lnl, int *warn)
+{
+  ARG_CHECK(inst, lnl != nullptr, "plk_edge_lnl: bad arguments");
+  if (!inst->shards.empty())
+  {  // all shards' reduction kernels are in flight before the first result is awaited
+    FOR_SHARDS(inst, edge_lnl_launch(sh, left, rght, pmat));
+    return finish_sharded(inst, lnl, nullptr, warn);
+  }
+  const int rc = edge_lnl_launch(inst, left, rght, pmat);
+  if (rc) return rc;
   return finish_reduction(inst, lnl, nullptr, warn);
 }
 
 // ---- K3 ------------------------------------------------------------------------------------------
 int plk_eigen_lr(plk_instance *inst, plk_side left, plk_side rght)
 {
+  if (!inst->shards.empty())
+  {
+    FOR_SHARDS(inst, plk_eigen_lr(sh, left, rght));
+    return PLK_OK;
+  }
+  USE_DEVICE(inst);
   int rc = check_side(inst, left, true);
   if (rc) return rc;
   rc = check_side(inst, rght, true);
@@ -1078,8 +1321,9 @@ int plk_eigen_lr(plk_instance *inst, plk_side left, plk_side rght)
 }
 
 // ---- K4 ------------------------------------------------------------------------------------------
-static int run_k4(plk_instance *inst, double l, int deriv, double *lnl, double *dlnl, int *warn)
+static int k4_launch(plk_instance *inst, double l, int deriv)
 {
+  USE_DEVICE(inst);
   if (!inst->eigen_ready)
   {
     inst->err = "plk_edge_lnl_dlnl / _eigen called before plk_eigen_lr (update_eigen_lr)";
@@ -1102,6 +1346,18 @@ static int run_k4(plk_instance *inst, double l, int deriv, double *lnl, double *
   }
   inst->launches++;
   CU_TRY(inst, cudaGetLastError());
+  return PLK_OK;
+}
+
+static int run_k4(plk_instance *inst, double l, int deriv, double *lnl, double *dlnl, int *warn)
+{
+  if (!inst->shards.empty())
+  {
+    FOR_SHARDS(inst, k4_launch(sh, l, deriv));
+    return finish_sharded(inst, lnl, dlnl, warn);
+  }
+  const int rc = k4_launch(inst, l, deriv);
+  if (rc) return rc;
   return finish_reduction(inst, lnl, dlnl, warn);
 }
 
@@ -1134,6 +1390,13 @@ static int ensure_tmp_clv(plk_instance *inst)
 int plk_get_clv(plk_instance *inst, int h, double *clv_out, int *scale_out)
 {
   ARG_CHECK(inst, h >= 0 && h < inst->cfg.n_clv, "clv handle out of range");
+  if (!inst->shards.empty())
+  {  // [site][catg][state]: a shard's block of patterns is a contiguous slice
+    const size_t per_site = (size_t)inst->cfg.ncatg * inst->cfg.ns;
+    FOR_SHARDS(inst, plk_get_clv(sh, h, clv_out ? clv_out + lo * per_site : nullptr, scale_out ? scale_out + lo : nullptr));
+    return PLK_OK;
+  }
+  USE_DEVICE(inst);
   ARG_CHECK(inst, inst->clv[h] != nullptr, "clv handle was never written");
   if (clv_out)
   {
@@ -1161,6 +1424,13 @@ int plk_get_clv(plk_instance *inst, int h, double *clv_out, int *scale_out)
 int plk_set_clv(plk_instance *inst, int h, const double *clv_in, const int *scale_in)
 {
   ARG_CHECK(inst, h >= 0 && h < inst->cfg.n_clv && clv_in, "clv handle out of range");
+  if (!inst->shards.empty())
+  {
+    const size_t per_site = (size_t)inst->cfg.ncatg * inst->cfg.ns;
+    FOR_SHARDS(inst, plk_set_clv(sh, h, clv_in + lo * per_site, scale_in ? scale_in + lo : nullptr));
+    return PLK_OK;
+  }
+  USE_DEVICE(inst);
   int rc = ensure_clv(inst, h);
   if (rc) return rc;
   if (inst->blocked)
@@ -1186,6 +1456,14 @@ int plk_set_clv(plk_instance *inst, int h, const double *clv_in, const int *scal
 
 int plk_get_site_lnl(plk_instance *inst, double *site_lnl, double *site_lk, double *site_lk_cat, int *fact)
 {
+  if (!inst->shards.empty())
+  {
+    const size_t nc = (size_t)inst->cfg.ncatg;
+    FOR_SHARDS(inst, plk_get_site_lnl(sh, site_lnl ? site_lnl + lo : nullptr, site_lk ? site_lk + lo : nullptr,
+                                      site_lk_cat ? site_lk_cat + lo * nc : nullptr, fact ? fact + lo : nullptr));
+    return PLK_OK;
+  }
+  USE_DEVICE(inst);
   const size_t P = inst->cfg.n_patterns;
   if (site_lnl)
     CU_TRY(inst, cudaMemcpyAsync(site_lnl, inst->d_site_lnl, P * sizeof(double), cudaMemcpyDeviceToHost, inst->stream));
@@ -1201,6 +1479,13 @@ int plk_get_site_lnl(plk_instance *inst, double *site_lnl, double *site_lk, doub
 
 int plk_get_dot_prod(plk_instance *inst, double *dot_prod)
 {
+  if (!inst->shards.empty())
+  {
+    const size_t per_site = (size_t)inst->cfg.ncatg * inst->cfg.ns;
+    FOR_SHARDS(inst, plk_get_dot_prod(sh, dot_prod ? dot_prod + lo * per_site : nullptr));
+    return PLK_OK;
+  }
+  USE_DEVICE(inst);
   ARG_CHECK(inst, dot_prod && inst->d_dot_prod, "dot_prod not computed yet");
   CU_TRY(inst, cudaMemcpyAsync(dot_prod, inst->d_dot_prod, clv_elems_plain(inst) * sizeof(double), cudaMemcpyDeviceToHost,
                                inst->stream));
@@ -1287,7 +1572,108 @@ int plk_comm_p2p_init(plk_instance *inst, int rank, int world, const void *handl
   inst->rank = rank;
   inst->world = world;
   inst->p2p = true;
+  inst->coll_seq = 0;       // all ranks wire their mailboxes at the same point of the program
+  CU_TRY(inst, cudaMemset(inst->d_mbox, 0, sizeof(P2pSlot) * 2 * world));
   inst->allreduce = false;  // the exchange now happens inside the reduction kernel
+  return PLK_OK;
+}
+
+// ---- single-process site sharding --------------------------------------------------------------------
+// One host thread, n_gpus devices, one ordinary instance per device over a contiguous block of patterns.
+// Every entry point fans out; the scalar-returning ones launch all shards' reduction kernels before the
+// first result is awaited.  With distinct devices that can reach each other the 24-byte exchange runs inside
+// the reduction kernels over NVLink peer memory (same mailbox protocol as plk_comm_p2p_*, peer access
+// enabled in-process instead of CUDA IPC); otherwise the host adds the partial sums in shard order.
+int plk_create_sharded(const plk_config *cfg, int n_gpus, const int *devices, plk_instance **out)
+{
+  if (!cfg || !out || n_gpus < 1 || n_gpus > 64)
+  {
+    g_create_error = "plk_create_sharded: bad arguments";
+    return PLK_ERR_ARG;
+  }
+  *out = nullptr;
+  if (cfg->n_patterns < n_gpus)
+  {
+    g_create_error = "plk_create_sharded: fewer patterns than shards";
+    return PLK_ERR_ARG;
+  }
+  plk_instance *grp = new plk_instance();
+  grp->cfg = *cfg;
+  grp->shard_lo.assign(n_gpus + 1, 0);
+  const long long P = cfg->n_patterns;
+  for (int i = 1; i < n_gpus; ++i)
+  {
+    long long lo = P * i / n_gpus;
+    if (P >= 64LL * n_gpus) lo &= ~31LL;  // whole 32-site chunks per shard when there are enough patterns
+    grp->shard_lo[i] = (int)lo;
+  }
+  grp->shard_lo[n_gpus] = (int)P;
+  g_multi_device = true;
+  bool distinct = n_gpus > 1;
+  for (int i = 0; i < n_gpus; ++i)
+  {
+    plk_config c = *cfg;
+    c.n_patterns = grp->shard_lo[i + 1] - grp->shard_lo[i];
+    c.device = devices ? devices[i] : i;
+    for (int j = 0; j < i; ++j)
+      if (grp->shards[j]->cfg.device == c.device) distinct = false;
+    plk_instance *sh = nullptr;
+    const int     rc = plk_create(&c, &sh);
+    if (rc)
+    {
+      plk_destroy(grp);
+      return rc;
+    }
+    grp->shards.push_back(sh);
+  }
+  if (distinct && !getenv("PLK_INPROC_HOSTSUM"))
+  {  // in-kernel exchange over peer memory if every pair of devices can map each other
+    bool ok = true;
+    for (int i = 0; i < n_gpus && ok; ++i)
+      for (int j = 0; j < n_gpus && ok; ++j)
+        if (i != j)
+        {
+          int can = 0;
+          if (cudaDeviceCanAccessPeer(&can, grp->shards[i]->cfg.device, grp->shards[j]->cfg.device) != cudaSuccess || !can)
+            ok = false;
+        }
+    if (ok)
+    {
+      std::vector<P2pSlot *> boxes(n_gpus, nullptr);
+      for (int i = 0; i < n_gpus && ok; ++i)
+      {
+        plk_instance *sh = grp->shards[i];
+        cudaSetDevice(sh->cfg.device);
+        for (int j = 0; j < n_gpus; ++j)
+          if (j != i)
+          {
+            const cudaError_t e = cudaDeviceEnablePeerAccess(grp->shards[j]->cfg.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = false;
+            (void)cudaGetLastError();
+          }
+        if (ok && (dev_alloc(sh, &sh->d_mbox, (size_t)2 * n_gpus) ||
+                   cudaMemset(sh->d_mbox, 0, sizeof(P2pSlot) * 2 * n_gpus) != cudaSuccess))
+          ok = false;
+        boxes[i] = sh->d_mbox;
+      }
+      for (int i = 0; i < n_gpus && ok; ++i)
+      {
+        plk_instance *sh = grp->shards[i];
+        cudaSetDevice(sh->cfg.device);
+        if (dev_alloc(sh, &sh->d_peers, (size_t)n_gpus) ||
+            cudaMemcpy(sh->d_peers, boxes.data(), sizeof(P2pSlot *) * n_gpus, cudaMemcpyHostToDevice) != cudaSuccess)
+          ok = false;
+        sh->rank = i;
+        sh->world = n_gpus;
+      }
+      if (ok)
+      {
+        for (plk_instance *sh : grp->shards) sh->p2p = true, sh->coll_seq = 0;
+        grp->inproc_p2p = true;
+      }
+    }
+  }
+  *out = grp;
   return PLK_OK;
 }
 
@@ -1303,8 +1689,19 @@ int plk_comm_set_allreduce(plk_instance *inst, int enable)
 }
 
 // ---- introspection -----------------------------------------------------------------------------------
-long long plk_launch_count(const plk_instance *inst) { return inst->launches; }
-size_t    plk_device_bytes(const plk_instance *inst) { return inst->bytes; }
-void     *plk_stream(plk_instance *inst) { return (void *)inst->stream; }
+long long plk_launch_count(const plk_instance *inst)
+{
+  long long n = inst->launches;
+  for (const plk_instance *sh : inst->shards) n += sh->launches;
+  return n;
+}
+size_t plk_device_bytes(const plk_instance *inst)
+{
+  size_t n = inst->bytes;
+  for (const plk_instance *sh : inst->shards) n += sh->bytes;
+  return n;
+}
+void *plk_stream(plk_instance *inst) { return (void *)(inst->shards.empty() ? inst->stream : inst->shards[0]->stream); }
+int   plk_n_shards(const plk_instance *inst) { return inst->shards.empty() ? 1 : (int)inst->shards.size(); }
 
 }  // extern "C"

@@ -651,6 +651,335 @@ __global__ void __launch_bounds__(kTravThreads, 2)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K1 fused traversal, 4 states, second generation ("op-major").  Same contract, lane map, TMA/mbarrier
+// descriptor ring and arithmetic as k_traverse_dna; what changes is the loop nest.  k_traverse_dna keeps
+// U items per thread in registers and walks the whole op list once per register-resident tile, so every
+// update pays its fixed cost (barrier wait, descriptor, 16 LDS.128 of P, kind dispatch) per tile pass and a
+// pattern count that is not a multiple of the resident capacity wastes a whole pass (measured: the fixed
+// cost is ~70 % of a U = 1 pass).  Here a block owns ONE contiguous tile of 32-item chunks for the whole
+// launch, and every compute warp loops over its chunks INSIDE each update:
+//   * fixed per-update cost paid once per warp, P held in registers across the chunk loop;
+//   * the previous update's result (the FWD operand) is forwarded through thread-private shared memory
+//     (two conflict-free 16-byte planes + the scaler per lane and chunk) instead of registers, so no value is
+//     live across updates and the five operand-kind specialisations share no register state;
+//   * global operands of chunk j+1 are loaded while chunk j is computed (L2 latency ~250 cycles);
+//   * quantisation is one chunk per warp instead of one pass per block.
+// Shared memory per block: kT2Stages ring stages + tile_chunks x 1152 bytes (dynamic).
+constexpr int kT2Stages = 4;
+constexpr int kT2ChunkBytes = 2 * 512 + 128;
+template <int NCATG>
+__host__ __device__ inline size_t t2_smem_bytes(int tile_chunks)
+{
+  return (size_t)kT2Stages * sizeof(TravStage<NCATG>) + (size_t)tile_chunks * kT2ChunkBytes;
+}
+
+// Data-path accessors of the op-major kernel: volatile (never dropped, never reordered among themselves) but
+// without a "memory" clobber, so that the surrounding scalars stay in registers.  Ordering against the
+// C++-level accesses is provided by the mbarrier wait / arrive asm statements, which do clobber memory.
+__device__ __forceinline__ void lds128(uint32_t a, double &x, double &y)
+{
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "r"(a));
+}
+__device__ __forceinline__ void sts128(uint32_t a, double x, double y)
+{
+  asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(a), "d"(x), "d"(y));
+}
+__device__ __forceinline__ int lds32(uint32_t a)
+{
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v)); }
+__device__ __forceinline__ double4a ldg256q(const double *p)
+{
+  double4a v;
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg256q(double *p, const double4a &v)
+{
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w));
+}
+__device__ __forceinline__ int ldg32q(const int *p)
+{
+  int v;
+  asm volatile("ld.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t ldg8q(const uint8_t *p)
+{
+  uint32_t v;
+  asm volatile("ld.global.u8 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg32q(int *p, int v) { asm volatile("st.global.s32 [%0], %1;" ::"l"(p), "r"(v)); }
+
+// operands of one chunk.  `fwa` = shared-memory address of this thread's forwarding slot of the chunk,
+// `off` = element offset of its 4 states in a blocked CLV (32-bit: a CLV of one shard stays below 2^31
+// doubles), `sidx` = site pattern.
+#define T2_LOAD(va, vb, scA, scB, rowA, rowB, fwa, off, sidx)    \
+  {                                                              \
+    if (KA == kSrcFwd)                                           \
+    {                                                            \
+      lds128((fwa), va.x, va.y);                                 \
+      lds128((fwa) + 512, va.z, va.w);                           \
+      scA = lds32(fws_of(fwa));                                  \
+    }                                                            \
+    else if (KA == kSrcSlot)                                     \
+    {                                                            \
+      va = ldg256q(c1 + (off));                                  \
+      scA = ldg32q(s1 + (sidx));                                 \
+    }                                                            \
+    else                                                         \
+      rowA = ldg8q(t1 + (sidx));                                 \
+    if (KB == kSrcSlot)                                          \
+    {                                                            \
+      vb = ldg256q(c2 + (off));                                  \
+      scB = ldg32q(s2 + (sidx));                                 \
+    }                                                            \
+    else                                                         \
+      rowB = ldg8q(t2 + (sidx));                                 \
+  }
+
+// one chunk: products, all-ones short cut, per-site maximum, rescaling, store + forward
+template <int NCATG, int KA, int KB>
+__device__ __forceinline__ void t2_chunk(const double4a &va, const double4a &vb, int scA, int scB, uint32_t rowA,
+                                         uint32_t rowB, const double (&pA)[16], const double (&pB)[16], uint32_t MAa,
+                                         uint32_t MBa, double *dst, int *dst_scale, uint32_t fwa, uint32_t fwsa, int cat,
+                                         int off, int sidx, bool live, int apply_scaling)
+{
+  constexpr int SW = 32 / NCATG;
+  // avx.c:575-587: both children all ones (only below fully ambiguous tips) -> the result is exactly 1.0.
+  // Cheap filter (tip row / first state); the full compare and the select only run when some lane passes it.
+  bool ones = (KA == kSrcTip) ? (rowA == (uint32_t)kTipRowAllOnes) : (__double2hiint(va.x) == 0x3FF00000);
+  ones = ones && ((KB == kSrcTip) ? (rowB == (uint32_t)kTipRowAllOnes) : (__double2hiint(vb.x) == 0x3FF00000));
+  const bool any_ones = __any_sync(0xffffffffu, ones);
+  if (any_ones)
+  {
+    if (KA != kSrcTip) ones = ones && all_one(va);
+    if (KB != kSrcTip) ones = ones && all_one(vb);
+  }
+  double uA[4], uB[4];
+  if (KA == kSrcTip)
+  {
+    const uint32_t t = MAa + (uint32_t)((cat * 16 + (int)rowA) * 32);
+    lds128(t, uA[0], uA[1]);
+    lds128(t + 16, uA[2], uA[3]);
+  }
+  else
+    matvec4(pA, va, uA);
+  if (KB == kSrcTip)
+  {
+    const uint32_t t = MBa + (uint32_t)((cat * 16 + (int)rowB) * 32);
+    lds128(t, uB[0], uB[1]);
+    lds128(t + 16, uB[2], uB[3]);
+  }
+  else
+    matvec4(pB, vb, uB);
+  double4a o;
+  o.x = uA[0] * uB[0];
+  o.y = uA[1] * uB[1];
+  o.z = uA[2] * uB[2];
+  o.w = uA[3] * uB[3];
+  if (any_ones)
+  {
+    if (ones) o.x = o.y = o.z = o.w = 1.0;
+  }
+  // avx.c:498-510: is the largest entry of the site below 2^-256?  All entries are >= 0, so the test is an
+  // integer compare of the exponent words (NaN counts as large, like the reference).
+  unsigned hmax = (unsigned)max(max(__double2hiint(o.x), __double2hiint(o.y)), max(__double2hiint(o.z), __double2hiint(o.w)));
+#pragma unroll
+  for (int d = SW; d < 32; d <<= 1) hmax = max(hmax, __shfl_xor_sync(0xffffffffu, hmax, d));
+  int        sco = scA + scB;
+  const bool resc = (hmax < 0x2FF00000u) && apply_scaling;
+  if (__any_sync(0xffffffffu, resc))
+  {
+    if (resc)
+    {
+      const double big = two_to_large();
+      o.x *= big;
+      o.y *= big;
+      o.z *= big;
+      o.w *= big;
+      sco += kLarge;
+    }
+  }
+  if (live)
+  {
+    stg256q(dst + off, o);
+    if (cat == 0) stg32q(dst_scale + sidx, sco);
+  }
+  sts128(fwa, o.x, o.y);
+  sts128(fwa + 512, o.z, o.w);
+  sts32(fwsa, sco);
+}
+
+template <int NCATG, int W, int KA, int KB>
+__device__ __forceinline__ void t2_run_op(const TravStage<NCATG> &stg, uint32_t fwa0, uint32_t fwsa0, int nch,
+                                          unsigned live_mask, int off0, int sidx0, int cat, int apply_scaling)
+{
+  constexpr int  SW = 32 / NCATG;
+  constexpr int  kFwdStride = W * kT2ChunkBytes;
+  constexpr int  kOffStride = W * 128;  // one chunk = 32 items x 4 doubles
+  constexpr int  kSiteStride = W * SW;
+  const double  *c1 = stg.op.c1, *c2 = stg.op.c2;
+  const int     *s1 = stg.op.s1, *s2 = stg.op.s2;
+  const uint8_t *t1 = stg.op.t1, *t2 = stg.op.t2;
+  double        *dst = stg.op.dst;
+  int           *dst_scale = stg.op.dst_scale;
+  const uint32_t MAa = smem_u32(stg.M[0]), MBa = smem_u32(stg.M[1]);
+  const uint32_t fws_delta = fwsa0 - fwa0;
+  auto           fws_of = [fws_delta](uint32_t fwa) { return fwa + fws_delta; };
+  double         pA[16], pB[16];
+  if (KA != kSrcTip)
+  {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) lds128(MAa + (uint32_t)(cat * 128 + q * 16), pA[2 * q], pA[2 * q + 1]);
+  }
+  if (KB != kSrcTip)
+  {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) lds128(MBa + (uint32_t)(cat * 128 + q * 16), pB[2 * q], pB[2 * q + 1]);
+  }
+  // two operand buffers used alternately: the loads of chunk j+1 are in flight while chunk j is computed
+  double4a va0, vb0, va1, vb1;
+  int      scA0 = 0, scB0 = 0, scA1 = 0, scB1 = 0;
+  uint32_t rowA0 = 0, rowB0 = 0, rowA1 = 0, rowB1 = 0;
+  va0.x = va0.y = va0.z = va0.w = 0.0;
+  vb0 = va1 = vb1 = va0;
+  uint32_t fwa = fwa0;
+  int      off = off0, sidx = sidx0;
+  if (nch > 0) T2_LOAD(va0, vb0, scA0, scB0, rowA0, rowB0, fwa, off, sidx)
+  for (int j = 0; j < nch; j += 2)
+  {
+    const bool has1 = (j + 1 < nch);
+    if (has1) T2_LOAD(va1, vb1, scA1, scB1, rowA1, rowB1, fwa + kFwdStride, off + kOffStride, sidx + kSiteStride)
+    t2_chunk<NCATG, KA, KB>(va0, vb0, scA0, scB0, rowA0, rowB0, pA, pB, MAa, MBa, dst, dst_scale, fwa, fws_of(fwa), cat, off,
+                            sidx, (live_mask >> j) & 1u, apply_scaling);
+    if (has1)
+    {
+      if (j + 2 < nch)
+        T2_LOAD(va0, vb0, scA0, scB0, rowA0, rowB0, fwa + 2 * kFwdStride, off + 2 * kOffStride, sidx + 2 * kSiteStride)
+      t2_chunk<NCATG, KA, KB>(va1, vb1, scA1, scB1, rowA1, rowB1, pA, pB, MAa, MBa, dst, dst_scale, fwa + kFwdStride,
+                              fws_of(fwa + kFwdStride), cat, off + kOffStride, sidx + kSiteStride,
+                              (live_mask >> (j + 1)) & 1u, apply_scaling);
+    }
+    fwa += 2 * kFwdStride;
+    off += 2 * kOffStride;
+    sidx += 2 * kSiteStride;
+  }
+}
+#undef T2_LOAD
+
+template <int NCATG, int W, int MINB>
+__global__ void __launch_bounds__((W + 1) * 32, MINB)
+    k_traverse_dna2(const OpDev *__restrict__ ops, int n_ops, int total_chunks, int tile_chunks, int n_tiles,
+                    const double *__restrict__ wght, int apply_scaling)
+{
+  static_assert(NCATG == 1 || NCATG == 2 || NCATG == 4 || NCATG == 8, "NCATG must divide the warp");
+  static_assert(NCATG != 8 || (W % 2) == 0, "8 categories: a chunk is half an 8-site block, W must be even");
+  constexpr int      S = kT2Stages;
+  constexpr int      SW = 32 / NCATG;
+  constexpr uint32_t PB = NCATG * 16 * sizeof(double);
+  constexpr uint32_t TB = NCATG * 64 * sizeof(double);
+  extern __shared__ __align__(128) unsigned char t2_smem[];
+  __shared__ __align__(8) uint64_t               full[S], empty[S];
+  TravStage<NCATG> *st = reinterpret_cast<TravStage<NCATG> *>(t2_smem);
+  unsigned char    *fwd = t2_smem + (size_t)S * sizeof(TravStage<NCATG>);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0)
+    for (int s = 0; s < S; ++s)
+    {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], W);
+    }
+  __syncthreads();
+  const int       rounds = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const long long total_it = (long long)rounds * n_ops;
+
+  if (warp == W)
+  {  // ---------------- producer warp (same protocol as k_traverse_dna)
+    for (long long base = 0; base < total_it; base += 32)
+    {
+      const long long    my = base + lane;
+      unsigned long long m1 = 0, m2 = 0;
+      int                kd = 0;
+      if (my < total_it)
+      {
+        const OpDev *o = ops + (my % n_ops);
+        m1 = (unsigned long long)o->P1;
+        m2 = (unsigned long long)o->P2;
+        kd = o->flags;
+      }
+      const int cnt = (int)min((long long)32, total_it - base);
+      for (int j = 0; j < cnt; ++j)
+      {
+        const unsigned long long a1 = __shfl_sync(0xffffffffu, m1, j), a2 = __shfl_sync(0xffffffffu, m2, j);
+        const int                kind = __shfl_sync(0xffffffffu, kd, j);
+        if (lane == 0)
+        {
+          const long long it = base + j;
+          const int       s = (int)(it % S);
+          const uint32_t  ph = (uint32_t)((it / S) & 1);
+          mbar_wait_backoff(&empty[s], ph ^ 1u);
+          const uint32_t b1 = ((kind & 3) == kSrcTip) ? TB : PB;
+          const uint32_t b2 = ((kind >> 2) == kSrcTip) ? TB : PB;
+          mbar_expect_tx(&full[s], (uint32_t)sizeof(OpDev) + b1 + b2);
+          tma_bulk_g2s(&st[s].op, ops + (it % n_ops), (uint32_t)sizeof(OpDev), &full[s]);
+          tma_bulk_g2s(st[s].M[0], (const void *)a1, b1, &full[s]);
+          tma_bulk_g2s(st[s].M[1], (const void *)a2, b2, &full[s]);
+        }
+        __syncwarp();
+      }
+    }
+    return;
+  }
+
+  // ---------------- compute warps: lane -> (site within the chunk, category)
+  const int cat = lane / SW, ls = lane % SW;
+  long long it = 0;
+  for (int r = 0; r < rounds; ++r)
+  {
+    const int tile = (int)blockIdx.x + r * (int)gridDim.x;
+    const int chunk0 = tile * tile_chunks;
+    const int n_chunks = min(tile_chunks, total_chunks - chunk0);
+    const int nch = (n_chunks > warp) ? (n_chunks - 1 - warp) / W + 1 : 0;  // chunks warp, warp + W, ... of the tile
+    const int sidx0 = (chunk0 + warp) * SW + ls;
+    const int      off0 = ((((sidx0 >> 3) * NCATG + cat) << 3) + (sidx0 & 7)) * 4;  // blocked layout, < 2^31 doubles
+    const uint32_t fwa0 = smem_u32(fwd + (size_t)warp * kT2ChunkBytes + lane * 16);  // this thread's slot, plane 0
+    const uint32_t fwsa0 = smem_u32(fwd + (size_t)warp * kT2ChunkBytes + 1024 + lane * 4);
+    unsigned        live_mask = 0u;
+    for (int j = 0; j < nch; ++j)
+      if (wght[sidx0 + j * (W * SW)] > DBL_MIN) live_mask |= 1u << j;  // avx.c:399 (arrays are padded with zero weights)
+
+    for (int k = 0; k < n_ops; ++k, ++it)
+    {
+      const int                s = (int)(it % S);
+      const TravStage<NCATG> &stg = st[s];
+      mbar_wait(&full[s], (uint32_t)((it / S) & 1));
+      const int kind = stg.op.flags, ka = kind & 3, kb = kind >> 2;
+      if (ka == kSrcFwd)
+      {
+        if (kb == kSrcTip)
+          t2_run_op<NCATG, W, kSrcFwd, kSrcTip>(stg, fwa0, fwsa0, nch, live_mask, off0, sidx0, cat, apply_scaling);
+        else
+          t2_run_op<NCATG, W, kSrcFwd, kSrcSlot>(stg, fwa0, fwsa0, nch, live_mask, off0, sidx0, cat, apply_scaling);
+      }
+      else if (ka == kSrcTip)
+        t2_run_op<NCATG, W, kSrcTip, kSrcTip>(stg, fwa0, fwsa0, nch, live_mask, off0, sidx0, cat, apply_scaling);
+      else if (kb == kSrcTip)
+        t2_run_op<NCATG, W, kSrcSlot, kSrcTip>(stg, fwa0, fwsa0, nch, live_mask, off0, sidx0, cat, apply_scaling);
+      else
+        t2_run_op<NCATG, W, kSrcSlot, kSrcSlot>(stg, fwa0, fwsa0, nch, live_mask, off0, sidx0, cat, apply_scaling);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+  }
+}
+
 // tip codes -> rows of the 20-state tip tables: state for one-hot codes, 20 for all-ones, 255 = general mask
 __global__ void k_codes_to_rows20(const uint8_t *__restrict__ codes, uint8_t *__restrict__ rows, size_t n,
                                   const uint32_t *__restrict__ tipmask)
@@ -1360,12 +1689,16 @@ struct ReduceOut
   double              *dev_out;   // [3]: values, warning as double (for the all-reduce)
   volatile ResultHost *host_out;
   unsigned long long   seq;
+  unsigned long long   coll_seq;  // sequence number of the cross-GPU exchange (reset when the mailboxes are wired)
   int                  publish;   // 1: write host_out here; 0: an all-reduce + k_publish follow
   // fused cross-GPU sum over NVLink peer memory (world > 1, p2p mode): every rank owns a mailbox
   // [2 parities][world senders] of P2pSlot; peers[q] is rank q's mailbox mapped into this process.
   struct P2pSlot     **peers;
   int                  rank, world;
 };
+
+constexpr unsigned long long kP2pTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;  // 20 s
+constexpr int                kWarnPeerTimeout = 2;  // bit 1 of ResultHost::warn: the cross-GPU exchange timed out
 
 struct __align__(32) P2pSlot
 {
@@ -1446,27 +1779,44 @@ __device__ __forceinline__ void block_reduce_finish(double (&v)[NV], int warn, c
       // reduction + collective in one kernel: post this rank's partial into every rank's mailbox
       // (remote stores over NVLink), wait for all ranks, add in RANK ORDER (bitwise identical result
       // on every rank).  Two parity slots: a rank can be at most one evaluation ahead of its readers.
-      const int par = (int)(ro.seq & 1ull);
+      const int par = (int)(ro.coll_seq & 1ull);
       for (int q = 0; q < ro.world; ++q)
       {
         P2pSlot *slot = ro.peers[q] + par * ro.world + ro.rank;
         slot->v[0] = r[0];
         slot->v[1] = r[1];
         slot->v[2] = (double)w;
-        st_release_sys_u64(&slot->seq, ro.seq);
+        st_release_sys_u64(&slot->seq, ro.coll_seq);
       }
       double acc[3] = {0.0, 0.0, 0.0};
-      for (int q = 0; q < ro.world; ++q)
+      bool   timed_out = false;
+      unsigned long long t_start = 0;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+      for (int q = 0; q < ro.world && !timed_out; ++q)
       {
         const P2pSlot *slot = ro.peers[ro.rank] + par * ro.world + q;
-        while (ld_acquire_sys_u64(&slot->seq) != ro.seq) __nanosleep(40);
+        unsigned       polls = 0;
+        while (ld_acquire_sys_u64(&slot->seq) != ro.coll_seq)
+        {
+          __nanosleep(40);
+          if ((++polls & 0x3ffu) == 0)
+          {  // a peer that died or fell out of step must not hang this GPU: give up after kP2pTimeoutNs
+            unsigned long long now = 0;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (now - t_start > kP2pTimeoutNs)
+            {
+              timed_out = true;
+              break;
+            }
+          }
+        }
         acc[0] += slot->v[0];
         acc[1] += slot->v[1];
         acc[2] += slot->v[2];
       }
       r[0] = acc[0];
       r[1] = acc[1];
-      w = acc[2] > 0.0 ? 1 : 0;
+      w = (acc[2] > 0.0 ? 1 : 0) | (timed_out ? kWarnPeerTimeout : 0);
     }
     ro.dev_out[0] = r[0];
     ro.dev_out[1] = r[1];

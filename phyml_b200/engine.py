@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import Iterable, Sequence
+from typing import Iterable, Optional, Sequence
 
 import numpy as np
 
@@ -45,7 +45,7 @@ EXPORTS = [
     "plk_set_pmat", "plk_get_pmat", "plk_update_partials", "plk_edge_lnl", "plk_eigen_lr",
     "plk_edge_lnl_dlnl", "plk_edge_lnl_eigen", "plk_get_clv", "plk_set_clv", "plk_get_site_lnl",
     "plk_get_dot_prod", "plk_comm_unique_id", "plk_comm_init", "plk_comm_set_allreduce",
-    "plk_comm_p2p_export", "plk_comm_p2p_init",
+    "plk_comm_p2p_export", "plk_comm_p2p_init", "plk_create_sharded", "plk_n_shards",
     "plk_launch_count", "plk_device_bytes", "plk_stream", "plk_version",
 ]
 
@@ -63,6 +63,8 @@ def load_library() -> C.CDLL:
     lib = C.CDLL(LIB_PATH)
     vp, dp, ip = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)
     lib.plk_create.argtypes = [C.POINTER(_Config), C.POINTER(vp)]
+    lib.plk_create_sharded.argtypes = [C.POINTER(_Config), C.c_int, C.POINTER(C.c_int), C.POINTER(vp)]
+    lib.plk_n_shards.argtypes = [vp]
     lib.plk_destroy.argtypes = [vp]
     lib.plk_destroy.restype = None
     lib.plk_last_error.argtypes = [vp]
@@ -119,13 +121,19 @@ class Engine:
     """One device instance (``plk_instance``): the B200 engine behind one tree."""
 
     def __init__(self, n_tips: int, n_pattern: int, ns: int, ncatg: int, n_clv: int, n_pmat: int,
-                 device: int = 0, apply_scaling: bool = True):
+                 device: int = 0, apply_scaling: bool = True, devices: Optional[Sequence[int]] = None):
+        """``devices``: site-shard the instance over these CUDA devices inside this process
+        (``plk_create_sharded``; a device may be listed more than once)."""
         self.lib = load_library()
         self.n_tips, self.P, self.ns, self.ncatg = n_tips, n_pattern, ns, ncatg
         self.n_clv, self.n_pmat = n_clv, n_pmat
         cfg = _Config(n_tips, n_pattern, ns, ncatg, n_clv, n_pmat, device, 0 if apply_scaling else 1)
         h = C.c_void_p()
-        rc = self.lib.plk_create(C.byref(cfg), C.byref(h))
+        if devices is None:
+            rc = self.lib.plk_create(C.byref(cfg), C.byref(h))
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = self.lib.plk_create_sharded(C.byref(cfg), len(devices), arr, C.byref(h))
         if rc != 0:
             raise EngineError(f"plk_create failed ({rc}): {self.lib.plk_last_error(None).decode()}")
         self.h = h
@@ -153,6 +161,10 @@ class Engine:
     @property
     def launch_count(self) -> int:
         return int(self.lib.plk_launch_count(self.h))
+
+    @property
+    def n_shards(self) -> int:
+        return int(self.lib.plk_n_shards(self.h))
 
     @property
     def device_bytes(self) -> int:
