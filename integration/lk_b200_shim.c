@@ -25,9 +25,25 @@
  * (p_lk_left / p_lk_rght / Pij_rr), never by edge number.  Tips are keyed by node number.
  *
  * Unsupported configurations abort like the BEAGLE hooks did (src/main.c:240-253): mixture trees
- * (is_mixt_tree), rooted trees (n_root), SCALE_RATE_SPECIFIC, M4, gamma_mgf_bl, ns > 32.
+ * (is_mixt_tree), rooted trees (n_root), SCALE_RATE_SPECIFIC, M4, gamma_mgf_bl, ns > 32, and any
+ * likelihood call on a tree that has no device instance (bootstrap replicates share the main tree's
+ * structures, src/utilities.c:4042) -- there is no silent CPU fallback.
  * Host-side readers of engine state: c_lnL_sorted / cur_site_lk / unscaled_site_lk_cat /
- * fact_sum_scale are mirrored after every Lk(NULL); CLVs and P-matrices stay on the device.
+ * fact_sum_scale are mirrored after every Lk(NULL); inside aLRT() (src/alrt.c:172), whose
+ * NNI_Neigh_BL reads c_lnL_sorted after edge-level calls (alrt.c:453,555,682), c_lnL_sorted is
+ * mirrored after every Lk(b) as well.  CLVs and P-matrices stay on the device.
+ *
+ * No host likelihood arena: Make_Tree_For_Lk asks posix_memalign for (3n-2)*P*ncatg*ns doubles
+ * (src/make.c:96-104; 3.8 GB at 100 taxa x 100k sites, 192 GB at 500 x 1M, and the size is computed in
+ * int arithmetic, so the reference itself aborts beyond 2^31 elements).  The shim interposes that one
+ * request and hands out an address-space reservation (mmap PROT_NONE | MAP_NORESERVE): the CLV and
+ * P-matrix pointers the reference carves from it (make.c:516-522,572-576,681-685) keep their role as
+ * buffer NAMES (they are the keys of the device handle tables) but no host memory backs them.
+ * Make_Edge_Lk is wrapped so that every edge carves from its own sub-range: the reference's int
+ * bump index (utilities.h:886) then never exceeds one edge's worth, whatever the alignment size.
+ *
+ * PLK_GPUS=N shards the instance over N devices of the box inside this one process
+ * (plk_create_sharded): the single t_tree of lk.c drives all of them.
  */
 #define _GNU_SOURCE
 #include <dlfcn.h>
@@ -35,6 +51,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <time.h>
 
 #include "utilities.h"
 #include "lk.h"
@@ -42,6 +60,7 @@
 #include "optimiz.h"
 #include "make.h"
 #include "free.h"
+#include "alrt.h"
 
 #include "../include/phyml_b200.h"
 
@@ -63,13 +82,95 @@ typedef struct
   int           pm_h[64];  /* deferred P-matrix updates: handle, branch length */
   double        pm_l[64];
   int           n_pm_queue;
-  double        model_print[8 + 2 * 32 + 2 * 16]; /* fingerprint of the uploaded model */
+  double        model_print[8 + 2 * 32 + 2 * 16]; /* scalars, eigenvalues, pi, rates of the uploaded model */
+  double       *model_uv;                          /* full copies of U and V (2 * ns * ns) */
   int           model_valid;
+  double       *wght_print;                        /* data->wght as uploaded (bootstrap-style in-place edits) */
   long long     n_lk, n_dlk, n_partial, n_flush, n_pmat;
+  char         *arena;      /* address-space reservation standing in for tree->big_lk_array */
+  size_t        arena_bytes, edge_span;
+  double        t_create, t_engine; /* wall-clock: instance creation time stamp, seconds spent inside the hooks */
 } shim_t;
 
 #define MAX_SHIMS 16
 static shim_t g_shims[MAX_SHIMS];
+static int    g_mirror_sites = 0; /* inside aLRT(): c_lnL_sorted is read after edge-level Lk() calls */
+
+/* wall-clock accounting of the time spent inside the hooks (outermost call only) */
+static int    g_depth = 0;
+static double g_t_enter = 0.0;
+static double now_s(void)
+{
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+#define HOOK_ENTER()                         \
+  do                                         \
+  {                                          \
+    if (g_depth++ == 0) g_t_enter = now_s(); \
+  } while (0)
+#define HOOK_LEAVE(sh)                                             \
+  do                                                               \
+  {                                                                \
+    if (--g_depth == 0 && (sh)) (sh)->t_engine += now_s() - g_t_enter; \
+  } while (0)
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Address-only likelihood arena.  The reference calls posix_memalign(&tree->big_lk_array, ...) once  */
+/* per tree (src/make.c:96-104); that request, and only that one, is answered with a reservation.    */
+static t_tree *g_arena_tree = NULL;
+static char   *g_arena_base = NULL;
+static size_t  g_arena_bytes = 0, g_arena_edge_span = 0;
+static int     g_arena_edge = 0;
+
+int posix_memalign(void **memptr, size_t alignment, size_t size)
+{
+  static int (*real)(void **, size_t, size_t) = NULL;
+  if (g_arena_tree && memptr == (void **)&g_arena_tree->big_lk_array)
+  {
+    const t_tree *tree = g_arena_tree;
+    const size_t  nc = (size_t)MAX(tree->mod->ras->n_catg, tree->mod->n_mixt_classes);
+    const size_t  ns = (size_t)tree->mod->ns;
+    /* per edge: Pij_rr, tPij_rr, p_lk_left, p_lk_rght (make.c:516-522,572-576,681-685), 64-bit arithmetic */
+    size_t span = (2 * (size_t)tree->mod->ras->n_catg * ns * ns + 2 * (size_t)tree->data->n_pattern * nc * ns) * sizeof(phydbl);
+    span = (span + 4095) & ~(size_t)4095;
+    g_arena_edge_span = span;
+    g_arena_bytes = span * (size_t)(2 * tree->n_otu);
+    g_arena_base = (char *)mmap(NULL, g_arena_bytes, PROT_NONE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    if (g_arena_base == (char *)MAP_FAILED)
+    {
+      g_arena_base = NULL;
+      return 12; /* ENOMEM */
+    }
+    g_arena_edge = 0;
+    *memptr = g_arena_base;
+    (void)alignment;
+    (void)size; /* the reference's own figure overflows int beyond 2^31 elements: not used */
+    return 0;
+  }
+  if (!real) real = (int (*)(void **, size_t, size_t))dlsym(RTLD_NEXT, "posix_memalign");
+  return real(memptr, alignment, size);
+}
+
+/* src/make.c:480-525: every edge carves its four buffers from its own sub-range of the reservation */
+void Make_Edge_Lk(t_edge *b, t_tree *tree)
+{
+  static void (*orig)(t_edge *, t_tree *) = NULL;
+  if (!orig) orig = (void (*)(t_edge *, t_tree *))dlsym(RTLD_NEXT, "Make_Edge_Lk");
+  if (tree == g_arena_tree && g_arena_base)
+  {
+    if (g_arena_edge >= 2 * tree->n_otu)
+    {
+      PhyML_Fprintf(stderr, "\n. phyml_b200: more Make_Edge_Lk calls than edges\n");
+      Exit("\n");
+    }
+    tree->big_lk_array = (phydbl *)(g_arena_base + (size_t)g_arena_edge * g_arena_edge_span);
+    tree->big_lk_array_pos = 0;
+    g_arena_edge++;
+  }
+  orig(b, tree);
+}
 
 static void die(const char *what, plk_instance *inst)
 {
@@ -110,6 +211,8 @@ static int map_get(slot_t *map, int cap, const void *key, int *counter, int limi
 static int clv_handle(shim_t *sh, const phydbl *p) { return map_get(sh->clv_map, sh->map_cap, p, &sh->n_clv, sh->clv_cap, "CLV"); }
 static int pm_handle(shim_t *sh, const phydbl *p) { return map_get(sh->pm_map, sh->map_cap, p, &sh->n_pm, sh->pm_cap, "P-matrix"); }
 
+static void flush(shim_t *sh);
+
 /* ------------------------------------------------------------------------------------------------ */
 static void upload_model_if_changed(shim_t *sh)
 {
@@ -128,10 +231,10 @@ static void upload_model_if_changed(shim_t *sh)
   k = 8 + 64;
   for (i = 0; i < nc; ++i) fp[k++] = mod->ras->gamma_rr->v[i];
   for (i = 0; i < nc; ++i) fp[k++] = mod->ras->gamma_r_proba->v[i];
-  /* eigenvectors change only together with the eigenvalues (Update_Eigen, models.c:881) plus U[0..] as a guard */
-  fp[5] = mod->eigen->r_e_vect[1];
-  fp[6] = mod->eigen->l_e_vect[ns > 1 ? ns : 0];
-  if (sh->model_valid && !memcmp(fp, sh->model_print, sizeof(fp))) return;
+  if (sh->model_valid && !memcmp(fp, sh->model_print, sizeof(fp)) &&
+      !memcmp(sh->model_uv, mod->eigen->r_e_vect, sizeof(double) * ns * ns) &&
+      !memcmp(sh->model_uv + ns * ns, mod->eigen->l_e_vect, sizeof(double) * ns * ns))
+    return;
   if (sh->n_pm_queue > 0)
   { /* P-matrices queued under the previous parameter values are computed with them, as the reference did */
     CK(plk_update_pmats(sh->inst, sh->n_pm_queue, sh->pm_h, sh->pm_l), sh);
@@ -142,7 +245,26 @@ static void upload_model_if_changed(shim_t *sh)
                    mod->l_min, mod->l_max, mod->br_len_mult->v),
      sh);
   memcpy(sh->model_print, fp, sizeof(fp));
+  memcpy(sh->model_uv, mod->eigen->r_e_vect, sizeof(double) * ns * ns);
+  memcpy(sh->model_uv + ns * ns, mod->eigen->l_e_vect, sizeof(double) * ns * ns);
   sh->model_valid = 1;
+}
+
+/* data->wght is edited in place by some callers (e.g. the bootstrap resampling of src/stats.c:2093-2133) */
+static void upload_weights_if_changed(shim_t *sh)
+{
+  const size_t n = sizeof(double) * (size_t)sh->tree->data->n_pattern;
+  if (!memcmp(sh->wght_print, sh->tree->data->wght, n)) return;
+  flush(sh);
+  CK(plk_set_pattern_weights(sh->inst, sh->tree->data->wght, sh->tree->data->invar), sh);
+  memcpy(sh->wght_print, sh->tree->data->wght, n);
+}
+
+static void no_instance(const char *fn)
+{
+  PhyML_Fprintf(stderr, "\n. phyml_b200: %s() was called on a tree without a device instance (trees that share another"
+                        "\n. tree's likelihood structures, e.g. bootstrap replicates, are not supported): use the CPU build.\n", fn);
+  Exit("\n");
 }
 
 /* Deferred work is executed as: all queued P-matrix updates in ONE batched launch, then all queued CLV
@@ -163,7 +285,7 @@ static void flush(shim_t *sh)
 
 static void check_supported(t_tree *tree)
 {
-  if (tree->is_mixt_tree == YES || tree->n_root != NULL || tree->mod->use_m4mod == YES ||
+  if (tree->is_mixt_tree == YES || tree->mixt_tree != NULL || tree->n_root != NULL || tree->mod->use_m4mod == YES ||
       tree->mod->gamma_mgf_bl == YES || tree->scaling_method != SCALE_FAST || tree->mod->ns > 32 ||
       (tree->io && tree->io->do_alias_subpatt == YES))
   {
@@ -196,11 +318,14 @@ void Make_Tree_For_Lk(t_tree *tree)
   static void (*orig)(t_tree *) = NULL;
   shim_t     *sh = NULL;
   plk_config  cfg;
-  int         i;
+  int         i, n_gpus;
   if (!orig) orig = (void (*)(t_tree *))dlsym(RTLD_NEXT, "Make_Tree_For_Lk");
-  orig(tree);
-  if (tree->is_mixt_tree == YES) return;
   check_supported(tree);
+  /* the reference's own allocation sequence, with the arena request answered by a reservation */
+  g_arena_tree = tree;
+  g_arena_base = NULL;
+  orig(tree);
+  g_arena_tree = NULL;
   for (i = 0; i < MAX_SHIMS; ++i)
     if (!g_shims[i].tree)
     {
@@ -214,6 +339,14 @@ void Make_Tree_For_Lk(t_tree *tree)
   }
   memset(sh, 0, sizeof(*sh));
   sh->tree = tree;
+  sh->arena = g_arena_base;
+  sh->arena_bytes = g_arena_bytes;
+  sh->edge_span = g_arena_edge_span;
+  if (sh->arena) tree->big_lk_array = (phydbl *)sh->arena;
+  sh->t_create = now_s();
+  sh->model_uv = (double *)calloc((size_t)2 * tree->mod->ns * tree->mod->ns, sizeof(double));
+  sh->wght_print = (double *)malloc(sizeof(double) * (size_t)tree->data->n_pattern);
+  memcpy(sh->wght_print, tree->data->wght, sizeof(double) * (size_t)tree->data->n_pattern);
   sh->clv_cap = 8 * tree->n_otu + 16;
   sh->pm_cap = 4 * tree->n_otu + 16;
   sh->map_cap = 4 * (sh->clv_cap + sh->pm_cap) + 7;
@@ -231,7 +364,8 @@ void Make_Tree_For_Lk(t_tree *tree)
   cfg.n_pmat = sh->pm_cap;
   cfg.device = getenv("PLK_DEVICE") ? atoi(getenv("PLK_DEVICE")) : 0;
   cfg.flags = (tree->apply_lk_scaling == YES) ? 0 : PLK_FLAG_NO_SCALING;
-  if (plk_create(&cfg, &sh->inst) != PLK_OK)
+  n_gpus = getenv("PLK_GPUS") ? atoi(getenv("PLK_GPUS")) : 1;
+  if ((n_gpus > 1 ? plk_create_sharded(&cfg, n_gpus, NULL, &sh->inst) : plk_create(&cfg, &sh->inst)) != PLK_OK)
   {
     PhyML_Fprintf(stderr, "\n. phyml_b200: plk_create failed: %s\n", plk_last_error(NULL));
     Exit("\n");
@@ -245,8 +379,10 @@ void Make_Tree_For_Lk(t_tree *tree)
     CK(plk_set_tip_vectors(sh->inst, tip->num, (b->rght == tip) ? b->p_lk_tip_r : b->p_lk_tip_l), sh);
   }
   if (getenv("PLK_SHIM_VERBOSE"))
-    PhyML_Printf("\n. phyml_b200: %s, instance for %d taxa x %d patterns, ns=%d ncatg=%d", plk_version(), tree->n_otu,
-                 tree->data->n_pattern, tree->mod->ns, tree->mod->ras->n_catg);
+    PhyML_Printf("\n. phyml_b200: %s, instance for %d taxa x %d patterns, ns=%d ncatg=%d on %d GPU(s); host likelihood "
+                 "arena: %.1f MB of address space reserved, 0 bytes committed",
+                 plk_version(), tree->n_otu, tree->data->n_pattern, tree->mod->ns, tree->mod->ras->n_catg,
+                 plk_n_shards(sh->inst), (double)sh->arena_bytes / 1e6);
 }
 
 void Free_Tree_Lk(t_tree *tree)
@@ -257,13 +393,26 @@ void Free_Tree_Lk(t_tree *tree)
   if (sh)
   {
     if (getenv("PLK_SHIM_VERBOSE"))
+    {
+      const double total = now_s() - sh->t_create;
       PhyML_Printf("\n. phyml_b200: Lk %lld  dLk %lld  Update_Partial_Lk %lld (in %lld launches)  Update_PMat %lld  "
                    "kernels %lld\n",
                    sh->n_lk, sh->n_dlk, sh->n_partial, sh->n_flush, sh->n_pmat, plk_launch_count(sh->inst));
+      PhyML_Printf(". phyml_b200: wall-clock since the instance was created %.2f s: %.2f s inside the likelihood hooks "
+                   "(engine + binding), %.2f s in the untouched host code (spr.c, optimiz.c, pars.c, ...)\n",
+                   total, sh->t_engine, total - sh->t_engine);
+    }
     plk_destroy(sh->inst);
+    if (sh->arena)
+    { /* free.c:391 frees big_lk_array: give it something free() accepts, then drop the reservation */
+      munmap(sh->arena, sh->arena_bytes);
+      tree->big_lk_array = (phydbl *)malloc(8);
+    }
     free(sh->clv_map);
     free(sh->pm_map);
     free(sh->queue);
+    free(sh->model_uv);
+    free(sh->wght_print);
     memset(sh, 0, sizeof(*sh));
   }
   orig(tree);
@@ -276,14 +425,9 @@ void Update_PMat_At_Given_Edge(t_edge *b_fcus, t_tree *tree)
   shim_t *sh = shim_of(tree);
   int     h;
   double  l;
-  if (!sh)
-  { /* trees without an instance (e.g. distance-based starting trees) keep the CPU path */
-    static void (*orig)(t_edge *, t_tree *) = NULL;
-    if (!orig) orig = (void (*)(t_edge *, t_tree *))dlsym(RTLD_NEXT, "Update_PMat_At_Given_Edge");
-    orig(b_fcus, tree);
-    return;
-  }
+  if (!sh) no_instance("Update_PMat_At_Given_Edge");
   assert(b_fcus && b_fcus->Pij_rr);
+  HOOK_ENTER();
   h = pm_handle(sh, b_fcus->Pij_rr);
   sh->n_pmat++;
   { /* a queued CLV update must see this matrix as it was when Update_Partial_Lk was called */
@@ -301,6 +445,7 @@ void Update_PMat_At_Given_Edge(t_edge *b_fcus, t_tree *tree)
       for (i = 0; i < ns; ++i) P[(size_t)c * ns * ns + i * ns + i] = 1.0;
     CK(plk_set_pmat(sh->inst, h, P), sh);
     free(P);
+    HOOK_LEAVE(sh);
     return;
   }
   upload_model_if_changed(sh);
@@ -311,12 +456,14 @@ void Update_PMat_At_Given_Edge(t_edge *b_fcus, t_tree *tree)
       if (sh->pm_h[i] == h)
       {
         sh->pm_l[i] = l;
+        HOOK_LEAVE(sh);
         return;
       }
     sh->pm_h[sh->n_pm_queue] = h;
     sh->pm_l[sh->n_pm_queue] = l;
     sh->n_pm_queue++;
   }
+  HOOK_LEAVE(sh);
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -328,13 +475,7 @@ void Update_Partial_Lk(t_tree *tree, t_edge *b, t_node *d)
   phydbl *p_lk = NULL, *p_lk_v1 = NULL, *p_lk_v2 = NULL, *Pij1 = NULL, *Pij2 = NULL, *tPij1 = NULL, *tPij2 = NULL;
   int    *sum_scale = NULL, *sum_scale_v1 = NULL, *sum_scale_v2 = NULL, *p_lk_loc = NULL;
   plk_op *op;
-  if (!sh)
-  {
-    static void (*orig)(t_tree *, t_edge *, t_node *) = NULL;
-    if (!orig) orig = (void (*)(t_tree *, t_edge *, t_node *))dlsym(RTLD_NEXT, "Update_Partial_Lk");
-    orig(tree, b, d);
-    return;
-  }
+  if (!sh) no_instance("Update_Partial_Lk");
   if (b->left == d && b->update_partial_lk_left == NO) return;
   if (b->rght == d && b->update_partial_lk_rght == NO) return;
   if (d->tax) return;
@@ -355,16 +496,12 @@ void Update_Partial_Lk(t_tree *tree, t_edge *b, t_node *d)
 void Update_Eigen_Lr(t_edge *b, t_tree *tree)
 {
   shim_t *sh = shim_of(tree);
-  if (!sh)
-  {
-    static void (*orig)(t_edge *, t_tree *) = NULL;
-    if (!orig) orig = (void (*)(t_edge *, t_tree *))dlsym(RTLD_NEXT, "Update_Eigen_Lr");
-    orig(b, tree);
-    return;
-  }
+  if (!sh) no_instance("Update_Eigen_Lr");
+  HOOK_ENTER();
   flush(sh);
   upload_model_if_changed(sh);
   CK(plk_eigen_lr(sh->inst, side_of(sh, b->left, b->p_lk_left), side_of(sh, b->rght, b->p_lk_rght)), sh);
+  HOOK_LEAVE(sh);
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -376,12 +513,7 @@ phydbl Lk(t_edge *b, t_tree *tree)
   int          warn = 0;
   double       lnl = 0.0;
   const int    full = (b == NULL);
-  if (!sh)
-  {
-    static phydbl (*orig)(t_edge *, t_tree *) = NULL;
-    if (!orig) orig = (phydbl(*)(t_edge *, t_tree *))dlsym(RTLD_NEXT, "Lk");
-    return orig(b, tree);
-  }
+  if (!sh) no_instance("Lk");
   tree->numerical_warning = NO;
   if (b == NULL && tree->mod->s_opt->curr_opt_free_rates == YES)
   { /* lk.c:458-463 */
@@ -403,6 +535,8 @@ phydbl Lk(t_edge *b, t_tree *tree)
     Update_Efrq(tree->mod);
     Update_Eigen(tree->mod);
   }
+  HOOK_ENTER();
+  if (b == NULL) upload_weights_if_changed(sh);
   upload_model_if_changed(sh);
 
   /* skip_tree_traversal (Optimiz_Alpha_And_Pinv, optimiz.c:2215-2222) only saves work in the
@@ -454,7 +588,10 @@ phydbl Lk(t_edge *b, t_tree *tree)
     CK(plk_get_site_lnl(sh->inst, tree->c_lnL_sorted, tree->cur_site_lk, tree->unscaled_site_lk_cat,
                         tree->fact_sum_scale),
        sh);
+  else if (g_mirror_sites) /* alrt.c:453,555,682 read c_lnL_sorted after Br_Len_Opt / Lk(b) */
+    CK(plk_get_site_lnl(sh->inst, tree->c_lnL_sorted, NULL, NULL, NULL), sh);
   sh->n_lk++;
+  HOOK_LEAVE(sh);
   return tree->c_lnL;
 }
 
@@ -465,15 +602,11 @@ phydbl dLk(phydbl *l, t_edge *b, t_tree *tree)
   shim_t *sh = shim_of(tree);
   double  lnl = 0.0, dlnl = 0.0;
   int     warn = 0;
-  if (!sh)
-  {
-    static phydbl (*orig)(phydbl *, t_edge *, t_tree *) = NULL;
-    if (!orig) orig = (phydbl(*)(phydbl *, t_edge *, t_tree *))dlsym(RTLD_NEXT, "dLk");
-    return orig(l, b, tree);
-  }
+  if (!sh) no_instance("dLk");
   tree->numerical_warning = NO;
   assert(isnan(*l) == FALSE);
   assert(b != NULL);
+  HOOK_ENTER();
   if (tree->update_eigen_lr == YES) Update_Eigen_Lr(b, tree);
   upload_model_if_changed(sh);
   CK(plk_edge_lnl_dlnl(sh->inst, l, &lnl, &dlnl, &warn), sh); /* clamps *l like lk.c:673-674 */
@@ -481,5 +614,18 @@ phydbl dLk(phydbl *l, t_edge *b, t_tree *tree)
   tree->c_lnL = lnl;
   if (warn) tree->numerical_warning = YES;
   sh->n_dlk++;
+  HOOK_LEAVE(sh);
   return tree->c_lnL;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* src/alrt.c:172: the branch-support tests read tree->c_lnL_sorted right after edge-level likelihood  */
+/* calls (NNI_Neigh_BL, alrt.c:453,555,682): mirror it after every Lk() while aLRT() runs             */
+void aLRT(t_tree *tree)
+{
+  static void (*orig)(t_tree *) = NULL;
+  if (!orig) orig = (void (*)(t_tree *))dlsym(RTLD_NEXT, "aLRT");
+  g_mirror_sites = 1;
+  orig(tree);
+  g_mirror_sites = 0;
 }

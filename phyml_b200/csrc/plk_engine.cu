@@ -448,7 +448,8 @@ int plk_create(const plk_config *cfg, plk_instance **out)
   CREATE_TRY(cudaStreamCreateWithFlags(&inst->stream, cudaStreamNonBlocking));
 
   const size_t P = (size_t)cfg->n_patterns;
-  inst->tip_stride = P;  // dense rows: the whole [n_tips][P] code matrix is one contiguous H2D copy
+  // rows padded to whole 128-byte lines (+ one 32-site chunk): the fused kernels stage them with 16-byte TMA units
+  inst->tip_stride = (P + kSitePad + 127) & ~(size_t)127;
   inst->pmat_elems = (size_t)cfg->ncatg * cfg->ns * cfg->ns;
   inst->pmat_stride = inst->pmat_elems + (cfg->ns == 4 ? (size_t)cfg->ncatg * 64 : 0) +
                       (cfg->ns == 20 ? (size_t)cfg->ncatg * (420 + 480) : 0);
@@ -985,11 +986,11 @@ static int launch_traverse2_t(plk_instance *inst, const OpDev *d_ops, int n_ops)
   const int    grid = std::min(n_tiles, slots);
   const size_t smem = t2_smem_bytes<NCATG>(tile_chunks);
   auto         kern = k_traverse_dna2<NCATG, W, MINB>;
-  static size_t smem_set = 0;  // per instantiation
-  if (smem > smem_set)
+  static size_t smem_set[64] = {};  // per instantiation and device
+  if (smem_set[inst->cfg.device & 63] == 0)
   {
     CU_TRY(inst, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(budget)));
-    smem_set = budget;
+    smem_set[inst->cfg.device & 63] = budget;
   }
   kern<<<grid, (W + 1) * 32, smem, inst->stream>>>(d_ops, n_ops, total_chunks, tile_chunks, n_tiles, inst->d_wght,
                                                     inst->apply_scaling);
@@ -1011,6 +1012,65 @@ static int launch_traverse2_nc(plk_instance *inst, const OpDev *d_ops, int n_ops
   case 5: return launch_traverse2_t<NCATG, (NCATG == 8) ? 4 : 5, 2>(inst, d_ops, n_ops);
   default: return launch_traverse2_t<NCATG, kW1, 1>(inst, d_ops, n_ops);
   }
+}
+
+// op-major tensor-pipe 4-state traversal (k_traverse_dna3): chunks of one 8-site block
+template <int NCATG, int W, int MINB>
+static int launch_traverse3_t(plk_instance *inst, const OpDev *d_ops, int n_ops)
+{
+  constexpr size_t kSmemPerSm = 227 * 1024;
+  const int        total_chunks = (inst->cfg.n_patterns + 7) / 8;
+  const size_t     budget = kSmemPerSm / MINB - 2048;
+  int              cap = (int)((budget - t3_smem_bytes<NCATG>(0)) / t3_chunk_bytes<NCATG>());
+  cap = std::min(std::min(cap, 32 * W), kT3MaxTileChunks) & ~1;  // live mask: 32 bits per warp; staged tip rows
+  const int       slots = inst->num_sms * MINB;
+  const long long per_round = (long long)slots * cap;
+  const int       rounds = (int)((total_chunks + per_round - 1) / per_round);
+  int             n_tiles = std::max(1, std::min(slots * rounds, total_chunks));
+  int             tile_chunks = (total_chunks + n_tiles - 1) / n_tiles;
+  tile_chunks = std::min((tile_chunks + 1) & ~1, cap);  // even: the TMA copies of the tip rows start on 16 bytes
+  n_tiles = (total_chunks + tile_chunks - 1) / tile_chunks;
+  const int     grid = std::min(n_tiles, slots);
+  const size_t  smem = t3_smem_bytes<NCATG>(tile_chunks);
+  auto          kern = k_traverse_dna3<NCATG, W, MINB>;
+  static size_t smem_set[64] = {};  // per instantiation and device
+  if (smem_set[inst->cfg.device & 63] == 0)
+  {
+    CU_TRY(inst, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(budget)));
+    smem_set[inst->cfg.device & 63] = budget;
+  }
+  kern<<<grid, (W + 1) * 32, smem, inst->stream>>>(d_ops, n_ops, total_chunks, tile_chunks, n_tiles, inst->d_wght,
+                                                    inst->apply_scaling);
+  inst->launches++;
+  CU_TRY(inst, cudaGetLastError());
+  return PLK_OK;
+}
+
+template <int NCATG>
+static int launch_traverse3_nc(plk_instance *inst, const OpDev *d_ops, int n_ops)
+{
+  switch (inst->t2_variant)
+  {
+  case 11: return launch_traverse3_t<NCATG, 15, 1>(inst, d_ops, n_ops);
+  case 12: return launch_traverse3_t<NCATG, 31, 1>(inst, d_ops, n_ops);
+  case 13: return launch_traverse3_t<NCATG, 7, 2>(inst, d_ops, n_ops);
+  case 14: return launch_traverse3_t<NCATG, 7, 3>(inst, d_ops, n_ops);
+  case 15: return launch_traverse3_t<NCATG, 11, 2>(inst, d_ops, n_ops);
+  default: return launch_traverse3_t<NCATG, 23, 1>(inst, d_ops, n_ops);
+  }
+}
+
+static int launch_traverse3(plk_instance *inst, const OpDev *d_ops, int n_ops)
+{
+  switch (inst->cfg.ncatg)
+  {
+  case 1: return launch_traverse3_nc<1>(inst, d_ops, n_ops);
+  case 2: return launch_traverse3_nc<2>(inst, d_ops, n_ops);
+  case 4: return launch_traverse3_nc<4>(inst, d_ops, n_ops);
+  case 8: return launch_traverse3_nc<8>(inst, d_ops, n_ops);
+  }
+  inst->err = "internal: unsupported ncatg for traversal kernel";
+  return PLK_ERR_ARG;
 }
 
 static int launch_traverse2(plk_instance *inst, const OpDev *d_ops, int n_ops)
@@ -1059,6 +1119,7 @@ int plk_update_partials(plk_instance *inst, int n_ops, const plk_op *ops)
   auto launch_fused = [&](const OpDev *d_ops, int n) {
     return (fused_dna && inst->dna_mma && nc <= 4) ? launch_traverse_mma(inst, d_ops, n)
            : (fused_dna && inst->trav_v1)          ? launch_traverse(inst, d_ops, n)
+           : (fused_dna && inst->t2_variant >= 10) ? launch_traverse3(inst, d_ops, n)
            : fused_dna                             ? launch_traverse2(inst, d_ops, n)
                                                    : launch_traverse_aa(inst, d_ops, n);
   };

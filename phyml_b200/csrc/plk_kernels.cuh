@@ -1291,6 +1291,349 @@ __global__ void __launch_bounds__(kTravThreads, 2)
 }
 
 // ------------------------------------------------------------------------------------------------
+// K1 fused traversal, 4 states, third generation: op-major like k_traverse_dna2, arithmetic on the FP64
+// tensor pipe like k_traverse_dna_mma.  ncu of k_traverse_dna2 (profiles/ncu_r2_dna2.md): 166 registers
+// (two 4x4 P matrices = 64 of them) allow 12 warps per SM, and with one chunk of look-ahead per warp the
+// kernel waits on L2 (long-scoreboard stalls 4.1 per issued instruction, issue slots 30 % busy).  With one
+// DMMA.8x8x4 per (8 sites, category, child) a P matrix costs ONE register pair per thread and a CLV word is
+// one double per thread, so the whole update state of a chunk is ~3*NCATG doubles: 3x the warps per SM, each
+// with two chunks in flight, and about half the instructions.
+//   lane = (g = lane>>2: site within the 8-site block, t = lane&3: state);  chunk = one 8-site block x NCATG
+//   A fragment: child CLV word (site g, state t), LDG.64 - 32 lanes read one contiguous 256-byte block
+//   B fragment: B[k=t][n=g] = P[c][g][t] for g < 4, else 0
+//   C fragment: lanes t < 2 hold states 2t, 2t+1 of site g (columns 4..7 are padding)
+// B200's DMMA accumulates as an ascending-k FMA chain from C = 0 (tools/probes/dmma_order.cu), i.e. it rounds
+// exactly like the reference's AVX_Matrix_Vect_Prod: bit-identical to the FMA kernels.
+// The previous update's result is forwarded through shared memory in C-fragment order (STS.128 by the
+// t < 2 lanes) and read back in A-fragment order (LDS.64, conflict-free): the layout change that cost the
+// register-forwarding variant two shuffles per category is free here.
+// Tip operands: the 1-byte tip-table rows of the block's tile (8 bytes per chunk) are part of what the
+// producer warp stages per update with a TMA bulk copy, several updates ahead.  (First version: LDG.U8 in the
+// compute warps one chunk ahead -- those loads miss L2, the 1 GB write stream evicts the 8 MB of tip rows
+// between evaluations, and their DRAM latency was the largest stall of the kernel, profiles/ncu_r2_dna3.md.)
+constexpr int kT3Stages = 4;
+constexpr int kT3MaxTileChunks = 256;  // 2 KB of tip rows per operand and stage
+template <int NCATG>
+struct __align__(128) T3Stage
+{
+  OpDev   op;  // 96 bytes
+  char    pad[128 - sizeof(OpDev)];
+  double  M[2][NCATG * 64];               // per child: P[cat][i][j] (NCATG*16) or TP[cat][mask][i] (NCATG*64)
+  uint8_t rows[2][kT3MaxTileChunks * 8];  // per tip child: tip-table row of every site of the tile
+};
+template <int NCATG>
+__host__ __device__ constexpr int t3_chunk_bytes()
+{
+  return NCATG * 256 + 128;
+}
+template <int NCATG>
+__host__ __device__ inline size_t t3_smem_bytes(int tile_chunks)
+{
+  return (size_t)kT3Stages * sizeof(T3Stage<NCATG>) + (size_t)tile_chunks * t3_chunk_bytes<NCATG>();
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t a)
+{
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ double lds64(uint32_t a)
+{
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ double ldg64q(const double *p)
+{
+  double v;
+  asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg128q(double *p, double x, double y)
+{
+  asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(x), "d"(y));
+}
+
+// operands of one chunk: fwa = this lane's 8-byte slot in the chunk's forwarding block (category 0),
+// fws = its scaler slot, goff = element offset of (8-site block, category 0) + lane, sidx = site pattern
+#define T3_LOAD(xA, xB, scA, scB, rowA, rowB, fwa, fws, goff, sidx)                  \
+  {                                                                                  \
+    if (KA == kSrcFwd)                                                               \
+    {                                                                                \
+      _Pragma("unroll") for (int c = 0; c < NCATG; ++c) xA[c] = lds64((fwa) + c * 256); \
+      scA = lds32(fws);                                                              \
+    }                                                                                \
+    else if (KA == kSrcSlot)                                                         \
+    {                                                                                \
+      _Pragma("unroll") for (int c = 0; c < NCATG; ++c) xA[c] = ldg64q(c1 + (goff) + c * 32); \
+      scA = ldg32q(s1 + (sidx));                                                     \
+    }                                                                                \
+    else                                                                             \
+      rowA = lds8(rwA + (sidx));                                                     \
+    if (KB == kSrcSlot)                                                              \
+    {                                                                                \
+      _Pragma("unroll") for (int c = 0; c < NCATG; ++c) xB[c] = ldg64q(c2 + (goff) + c * 32); \
+      scB = ldg32q(s2 + (sidx));                                                     \
+    }                                                                                \
+    else                                                                             \
+      rowB = lds8(rwB + (sidx));                                                     \
+  }
+
+template <int NCATG, int KA, int KB>
+__device__ __forceinline__ void t3_chunk(const double (&xA)[NCATG], const double (&xB)[NCATG], int scA, int scB,
+                                         uint32_t rowA, uint32_t rowB, const double (&bA)[NCATG],
+                                         const double (&bB)[NCATG], uint32_t MAa, uint32_t MBa, double *dst,
+                                         int *dst_scale, uint32_t fwa, uint32_t fws, int lane, int goff, int sidx,
+                                         bool live, int apply_scaling)
+{
+  const int t = lane & 3;
+  // avx.c:575-587: both children all ones (only below fully ambiguous tips) -> the result is exactly 1.0.
+  // Conservative filter on child A (tip row / exponent word of any category); exact test in the slow path.
+  bool maybe = false;
+  if (KA == kSrcTip)
+    maybe = (rowA == (uint32_t)kTipRowAllOnes);
+  else
+  {
+#pragma unroll
+    for (int c = 0; c < NCATG; ++c) maybe = maybe || (__double2hiint(xA[c]) == 0x3FF00000);
+  }
+  const bool any_ones = __any_sync(0xffffffffu, maybe);
+  double     o0[NCATG], o1[NCATG];
+#pragma unroll
+  for (int c = 0; c < NCATG; ++c)
+  {
+    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+    if (KA == kSrcTip)
+    {
+      if (t < 2) lds128(MAa + (uint32_t)(((c * 16 + (int)rowA) * 4 + 2 * t) * 8), a0, a1);
+    }
+    else
+      dmma884(a0, a1, xA[c], bA[c]);
+    if (KB == kSrcTip)
+    {
+      if (t < 2) lds128(MBa + (uint32_t)(((c * 16 + (int)rowB) * 4 + 2 * t) * 8), b0, b1);
+    }
+    else
+      dmma884(b0, b1, xB[c], bB[c]);
+    o0[c] = a0 * b0;
+    o1[c] = a1 * b1;
+  }
+  if (any_ones)
+  {
+#pragma unroll
+    for (int c = 0; c < NCATG; ++c)
+    {
+      const bool     pa = (KA == kSrcTip) ? (rowA == (uint32_t)kTipRowAllOnes) : (xA[c] == 1.0);
+      const bool     pb = (KB == kSrcTip) ? (rowB == (uint32_t)kTipRowAllOnes) : (xB[c] == 1.0);
+      const unsigned bal = __ballot_sync(0xffffffffu, pa && pb);
+      if (((bal >> (lane & ~3)) & 0xFu) == 0xFu) o0[c] = o1[c] = 1.0;
+    }
+  }
+  // avx.c:498-510: per-site maximum over all categories and states as an exponent-word compare (all entries
+  // are >= 0; NaN counts as large, like the reference); the t >= 2 lanes hold padding zeros
+  int hmax = 0;
+#pragma unroll
+  for (int c = 0; c < NCATG; ++c) hmax = max(hmax, max(__double2hiint(o0[c]), __double2hiint(o1[c])));
+  hmax = max(hmax, __shfl_xor_sync(0xffffffffu, hmax, 1));
+  int        sco = scA + scB;
+  const bool resc = (t < 2) && ((unsigned)hmax < 0x2FF00000u) && apply_scaling;
+  if (__any_sync(0xffffffffu, resc))
+  {
+    if (resc)
+    {
+      const double big = two_to_large();
+#pragma unroll
+      for (int c = 0; c < NCATG; ++c)
+      {
+        o0[c] *= big;
+        o1[c] *= big;
+      }
+      sco += kLarge;
+    }
+  }
+  if (t < 2)
+  {
+    if (live)
+    {
+#pragma unroll
+      for (int c = 0; c < NCATG; ++c) stg128q(dst + goff + t + c * 32, o0[c], o1[c]);
+      if (t == 0) stg32q(dst_scale + sidx, sco);
+    }
+#pragma unroll
+    for (int c = 0; c < NCATG; ++c) sts128(fwa + t * 8 + c * 256, o0[c], o1[c]);
+    sts32(fws, sco);  // only the t == 0 copy is ever consumed (scalers are per site)
+  }
+}
+
+template <int NCATG, int W, int KA, int KB>
+__device__ __forceinline__ void t3_run_op(const T3Stage<NCATG> &stg, uint32_t fwa0, uint32_t fws0, int nch,
+                                          unsigned live_mask, int goff0, int sidx0, int tile_site0, int lane,
+                                          int apply_scaling)
+{
+  constexpr int  kFwdStride = W * t3_chunk_bytes<NCATG>();
+  constexpr int  kOffStride = W * NCATG * 32;  // one chunk = 8 sites x NCATG x 4 doubles
+  constexpr int  kSiteStride = W * 8;
+  const double  *c1 = stg.op.c1, *c2 = stg.op.c2;
+  const int     *s1 = stg.op.s1, *s2 = stg.op.s2;
+  // staged tip rows, biased so that they are indexed by the global site pattern like the CLV operands
+  const uint32_t rwA = smem_u32(stg.rows[0]) - (uint32_t)tile_site0, rwB = smem_u32(stg.rows[1]) - (uint32_t)tile_site0;
+  double        *dst = stg.op.dst;
+  int           *dst_scale = stg.op.dst_scale;
+  const uint32_t MAa = smem_u32(stg.M[0]), MBa = smem_u32(stg.M[1]);
+  const int      g = lane >> 2, t = lane & 3;
+  double         bA[NCATG], bB[NCATG];
+#pragma unroll
+  for (int c = 0; c < NCATG; ++c)
+  {
+    bA[c] = (KA != kSrcTip && g < 4) ? lds64(MAa + (uint32_t)((c * 16 + g * 4 + t) * 8)) : 0.0;
+    bB[c] = (KB != kSrcTip && g < 4) ? lds64(MBa + (uint32_t)((c * 16 + g * 4 + t) * 8)) : 0.0;
+  }
+  double   xA0[NCATG], xB0[NCATG], xA1[NCATG], xB1[NCATG];
+  int      scA0 = 0, scB0 = 0, scA1 = 0, scB1 = 0;
+  uint32_t rowA0 = 0, rowB0 = 0, rowA1 = 0, rowB1 = 0;
+#pragma unroll
+  for (int c = 0; c < NCATG; ++c) xA0[c] = xB0[c] = xA1[c] = xB1[c] = 0.0;
+  uint32_t fwa = fwa0, fws = fws0;
+  int      goff = goff0, sidx = sidx0;
+  if (nch > 0) T3_LOAD(xA0, xB0, scA0, scB0, rowA0, rowB0, fwa, fws, goff, sidx)
+  for (int j = 0; j < nch; j += 2)
+  {
+    const bool has1 = (j + 1 < nch);
+    if (has1)
+      T3_LOAD(xA1, xB1, scA1, scB1, rowA1, rowB1, fwa + kFwdStride, fws + kFwdStride, goff + kOffStride, sidx + kSiteStride)
+    t3_chunk<NCATG, KA, KB>(xA0, xB0, scA0, scB0, rowA0, rowB0, bA, bB, MAa, MBa, dst, dst_scale, fwa, fws, lane, goff, sidx,
+                            (live_mask >> j) & 1u, apply_scaling);
+    if (has1)
+    {
+      if (j + 2 < nch)
+        T3_LOAD(xA0, xB0, scA0, scB0, rowA0, rowB0, fwa + 2 * kFwdStride, fws + 2 * kFwdStride, goff + 2 * kOffStride,
+                sidx + 2 * kSiteStride)
+      t3_chunk<NCATG, KA, KB>(xA1, xB1, scA1, scB1, rowA1, rowB1, bA, bB, MAa, MBa, dst, dst_scale, fwa + kFwdStride,
+                              fws + kFwdStride, lane, goff + kOffStride, sidx + kSiteStride, (live_mask >> (j + 1)) & 1u,
+                              apply_scaling);
+    }
+    fwa += 2 * kFwdStride;
+    fws += 2 * kFwdStride;
+    goff += 2 * kOffStride;
+    sidx += 2 * kSiteStride;
+  }
+}
+#undef T3_LOAD
+
+template <int NCATG, int W, int MINB>
+__global__ void __launch_bounds__((W + 1) * 32, MINB)
+    k_traverse_dna3(const OpDev *__restrict__ ops, int n_ops, int total_chunks, int tile_chunks, int n_tiles,
+                    const double *__restrict__ wght, int apply_scaling)
+{
+  constexpr int      S = kT3Stages;
+  constexpr uint32_t PB = NCATG * 16 * sizeof(double);
+  constexpr uint32_t TB = NCATG * 64 * sizeof(double);
+  extern __shared__ __align__(128) unsigned char t3_smem[];
+  __shared__ __align__(8) uint64_t               full[S], empty[S];
+  T3Stage<NCATG> *st = reinterpret_cast<T3Stage<NCATG> *>(t3_smem);
+  unsigned char  *fwd = t3_smem + (size_t)S * sizeof(T3Stage<NCATG>);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0)
+    for (int s = 0; s < S; ++s)
+    {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], W);
+    }
+  __syncthreads();
+  const int       rounds = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const long long total_it = (long long)rounds * n_ops;
+
+  if (warp == W)
+  {  // ---------------- producer warp (same protocol as k_traverse_dna)
+    for (long long base = 0; base < total_it; base += 32)
+    {
+      const long long    my = base + lane;
+      unsigned long long m1 = 0, m2 = 0, r1 = 0, r2 = 0;
+      int                kd = 0;
+      if (my < total_it)
+      {
+        const OpDev *o = ops + (my % n_ops);
+        m1 = (unsigned long long)o->P1;
+        m2 = (unsigned long long)o->P2;
+        r1 = (unsigned long long)o->t1;
+        r2 = (unsigned long long)o->t2;
+        kd = o->flags;
+      }
+      const int cnt = (int)min((long long)32, total_it - base);
+      for (int j = 0; j < cnt; ++j)
+      {
+        const unsigned long long a1 = __shfl_sync(0xffffffffu, m1, j), a2 = __shfl_sync(0xffffffffu, m2, j);
+        const unsigned long long q1 = __shfl_sync(0xffffffffu, r1, j), q2 = __shfl_sync(0xffffffffu, r2, j);
+        const int                kind = __shfl_sync(0xffffffffu, kd, j);
+        if (lane == 0)
+        {
+          const long long it = base + j;
+          const int       s = (int)(it % S);
+          const uint32_t  ph = (uint32_t)((it / S) & 1);
+          const int       tile = (int)blockIdx.x + (int)(it / n_ops) * (int)gridDim.x;
+          const int       chunk0 = tile * tile_chunks;
+          // tip rows of the tile: whole 16-byte units (tiles start on even chunks, rows are padded)
+          const uint32_t rb = (uint32_t)((min(tile_chunks, total_chunks - chunk0) * 8 + 15) & ~15);
+          const bool     tipA = (kind & 3) == kSrcTip, tipB = (kind >> 2) == kSrcTip;
+          mbar_wait_backoff(&empty[s], ph ^ 1u);
+          const uint32_t b1 = tipA ? TB : PB;
+          const uint32_t b2 = tipB ? TB : PB;
+          mbar_expect_tx(&full[s], (uint32_t)sizeof(OpDev) + b1 + b2 + (tipA ? rb : 0u) + (tipB ? rb : 0u));
+          tma_bulk_g2s(&st[s].op, ops + (it % n_ops), (uint32_t)sizeof(OpDev), &full[s]);
+          tma_bulk_g2s(st[s].M[0], (const void *)a1, b1, &full[s]);
+          tma_bulk_g2s(st[s].M[1], (const void *)a2, b2, &full[s]);
+          if (tipA) tma_bulk_g2s(st[s].rows[0], (const void *)(q1 + (unsigned long long)chunk0 * 8ull), rb, &full[s]);
+          if (tipB) tma_bulk_g2s(st[s].rows[1], (const void *)(q2 + (unsigned long long)chunk0 * 8ull), rb, &full[s]);
+        }
+        __syncwarp();
+      }
+    }
+    return;
+  }
+
+  // ---------------- compute warps
+  long long it = 0;
+  for (int r = 0; r < rounds; ++r)
+  {
+    const int tile = (int)blockIdx.x + r * (int)gridDim.x;
+    const int chunk0 = tile * tile_chunks;
+    const int n_chunks = min(tile_chunks, total_chunks - chunk0);
+    const int nch = (n_chunks > warp) ? (n_chunks - 1 - warp) / W + 1 : 0;  // chunks warp, warp + W, ... of the tile
+    const int sidx0 = (chunk0 + warp) * 8 + (lane >> 2);
+    const int goff0 = (chunk0 + warp) * NCATG * 32 + lane;  // blocked layout, < 2^31 doubles
+    const uint32_t cbase = smem_u32(fwd + (size_t)warp * t3_chunk_bytes<NCATG>());
+    const uint32_t fwa0 = cbase + lane * 8, fws0 = cbase + NCATG * 256 + lane * 4;
+    unsigned       live_mask = 0u;
+    for (int j = 0; j < nch; ++j)
+      if (wght[sidx0 + j * (W * 8)] > DBL_MIN) live_mask |= 1u << j;  // avx.c:399 (arrays are padded with zero weights)
+
+    for (int k = 0; k < n_ops; ++k, ++it)
+    {
+      const int                s = (int)(it % S);
+      const T3Stage<NCATG> &stg = st[s];
+      mbar_wait(&full[s], (uint32_t)((it / S) & 1));
+      const int kind = stg.op.flags, ka = kind & 3, kb = kind >> 2;
+      if (ka == kSrcFwd)
+      {
+        if (kb == kSrcTip)
+          t3_run_op<NCATG, W, kSrcFwd, kSrcTip>(stg, fwa0, fws0, nch, live_mask, goff0, sidx0, chunk0 * 8, lane, apply_scaling);
+        else
+          t3_run_op<NCATG, W, kSrcFwd, kSrcSlot>(stg, fwa0, fws0, nch, live_mask, goff0, sidx0, chunk0 * 8, lane, apply_scaling);
+      }
+      else if (ka == kSrcTip)
+        t3_run_op<NCATG, W, kSrcTip, kSrcTip>(stg, fwa0, fws0, nch, live_mask, goff0, sidx0, chunk0 * 8, lane, apply_scaling);
+      else if (kb == kSrcTip)
+        t3_run_op<NCATG, W, kSrcSlot, kSrcTip>(stg, fwa0, fws0, nch, live_mask, goff0, sidx0, chunk0 * 8, lane, apply_scaling);
+      else
+        t3_run_op<NCATG, W, kSrcSlot, kSrcSlot>(stg, fwa0, fws0, nch, live_mask, goff0, sidx0, chunk0 * 8, lane, apply_scaling);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K1 fused traversal, 20 states, on the FP64 tensor pipe (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4).
 // The per-category update  dst[s][i] = (sum_j P1[i][j] x1[s][j]) * (sum_j P2[i][j] x2[s][j])  is the
 // dense contraction (sites x 20) . (20 x 20): sites are the M dimension (8 per m-tile), output states

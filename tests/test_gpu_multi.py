@@ -85,3 +85,41 @@ def test_two_gpu_sharded_lnl(mode):
         assert abs(r[3] - ref.c_dlnL) <= 1e-9 * max(1.0, abs(ref.c_dlnL))
     if mode == "p2p":
         assert res[0][1:] == res[1][1:], "rank-order addition must give bitwise identical results on all ranks"
+
+
+def test_single_process_sharded_instance_two_devices():
+    """plk_create_sharded over devices 0 and 1 in THIS process (the way lk.c's single t_tree drives a box,
+    SURVEY.md section 8e): the exchange runs inside the reduction kernels over peer memory enabled in-process;
+    lnL / dLk / CLV read-backs must equal the single-device instance's."""
+    import numpy as np
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from phyml_b200.engine import Engine
+    from phyml_b200.lk import LkTree
+
+    tree, m, pat = _case()
+    args = (tree.n_otu, pat.n_pattern, 4, 4, tree.n_clv_handles, tree.n_edges)
+    one = LkTree(tree, pat, m, Engine(*args))
+    two = LkTree(tree, pat, m, Engine(*args, devices=[0, 1]))
+    assert two.eng.n_shards == 2
+    for t in (one, two):
+        t.Set_Both_Sides(1)
+    a, b = one.Lk(), two.Lk()
+    assert abs(a - b) <= 1e-12 * abs(a)
+    for e in (0, 3, tree.n_edges - 1):
+        assert abs(one.Lk(e) - two.Lk(e)) <= 1e-12 * abs(a)
+    for t in (one, two):
+        t.Set_Update_Eigen_Lr(1)
+        t.Lk(3)
+        t.Set_Update_Eigen_Lr(0)
+        t.dLk(0.05, 3)
+    assert abs(one.c_lnL - two.c_lnL) <= 1e-12 * abs(one.c_lnL)
+    assert abs(one.c_dlnL - two.c_dlnL) <= 1e-9 * max(1.0, abs(one.c_dlnL))
+    h = tree.post_order_ops()[5].dst
+    ca, sa = one.eng.get_clv(h)
+    cb, sb = two.eng.get_clv(h)
+    assert np.array_equal(ca, cb) and np.array_equal(sa, sb)
+    s1, s2 = one.eng.get_site_lnl(), two.eng.get_site_lnl()
+    np.testing.assert_allclose(s1["site_lnl"], s2["site_lnl"], rtol=1e-13)
