@@ -5,10 +5,17 @@
     python bench.py --impl reference --gpus N --steps K --warmup W
 
 A step = one full-tree lnL evaluation Lk(NULL) (all P-matrices, n-2 CLV updates in post-order,
-edge reduction) of a fixed random tree on a synthetic alignment:
+edge reduction) of a fixed random tree on a synthetic alignment (phyml_b200/workloads.py):
   N=1 workload: BASELINE.json configs[1], DNA 100 taxa x 100 000 sites, GTR+G4.
-  N>1: each rank owns a contiguous block of 100 000 sites (weak scaling, site sharding); the only
-       exchange is one ncclAllReduce of the partial lnL per evaluation.
+  N>1 workload: BASELINE.json configs[3], DNA 500 taxa x 1 000 000 sites, GTR+G4, STRONG scaling:
+       the alignment's 16 column blocks are split evenly over the ranks (site sharding); the only
+       exchange is the sum of the per-rank partial lnL, fused into the reduction kernel over NVLink
+       peer memory (PLK_COMM=nccl: one ncclAllReduce per evaluation).
+  Both are evaluated under the reference's own eigen system for that CLI and compared with the
+  reference's own lnL on the SAME alignment and tree (tests/golden/big/*.npz -> `lnL_reference`,
+  `parity_rel_err`).
+  The N=1 line also carries, under `secondary`, BASELINE configs[2] (AA 200 x 50 000, the 20-state
+  tensor-pipe path) and configs[3] on ONE GPU (the strong-scaling base of the N>1 lines).
 metric = site*edge updates/s = patterns * (n_taxa - 2) * evaluations / s, whole job.
 Prints ONE JSON line (rank 0).
 """
@@ -27,30 +34,15 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from phyml_b200 import alignment, model as pmodel  # noqa: E402
-from phyml_b200.tree import Tree  # noqa: E402
+from phyml_b200 import alignment, workloads as wl  # noqa: E402
 
 METRIC = "site_edge_updates_per_s"
 UNIT = "site*edge-updates/s"
-
-WORKLOADS = {
-    # name: (ns, n_taxa, sites_per_gpu, description)
-    "dna_100x100k": (4, 100, 100_000, "synthetic DNA 100 taxa x 100000 sites, GTR+G4, fixed random tree (BASELINE configs[1])"),
-    "aa_200x50k": (20, 200, 50_000, "synthetic AA 200 taxa x 50000 sites, LG+G4 (BASELINE configs[2])"),
-    "dna_500x125k": (4, 500, 125_000, "synthetic DNA 500 taxa x 125000 sites per GPU, GTR+G4 (BASELINE configs[3] sharded 8 ways)"),
-    "dna_100x50k": (4, 100, 50_000, "synthetic DNA 100 taxa x 50000 sites, GTR+G4 (BASELINE configs[4] alignment)"),
-    "dna_16x4k": (4, 16, 4_096, "tiny DNA smoke workload"),
-}
+PARITY_RTOL = 1e-9   # BASELINE.json north_star
 
 
-def make_workload(name, rank, world, seed=1):
-    ns, n_taxa, sites, desc = WORKLOADS[name]
-    tree = Tree.random(n_taxa, seed=seed)
-    m = pmodel.gtr(alpha=0.5) if ns == 4 else pmodel.lg_from_fixture(alpha=0.5)
-    # every rank simulates its own block of columns (same tree, different seed): site sharding
-    codes = alignment.simulate(tree, m, sites, seed=1000 + rank)
-    pat = alignment.compress(codes, ns)
-    return tree, m, pat, codes, desc
+def default_workload(gpus):
+    return "dna_100x100k" if gpus == 1 else "dna_500x1M"
 
 
 def k1_algorithmic_bytes(tree, ops, P, ns, ncatg):
@@ -110,22 +102,44 @@ class ClockSampler(threading.Thread):
         return out
 
 
+def load_peaks():
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk_path):
+        try:
+            return json.load(open(pk_path))
+        except Exception:
+            pass
+    return {}
+
+
+def k1_kernel_name(ns, ncatg):
+    if ns == 4 and ncatg in (1, 2, 4, 8):
+        v = os.environ.get("PLK_T2_VARIANT")
+        if os.environ.get("PLK_TRAV_V1", "0") not in ("", "0"):
+            return "k_traverse_dna<%d,2>" % ncatg
+        if v is not None and int(v) < 10:
+            return "k_traverse_dna2<%d>" % ncatg
+        return "k_traverse_dna3<%d> (DMMA.8x8x4)" % ncatg
+    if ns == 20:
+        return "k_traverse_aa (DMMA.8x8x4)"
+    return "k_partial_generic"
+
+
 # ======================================================================================================
-def run_b200(args):
+def measure(name, rank, world, local, steps, warmup, e2e=True, clocks=True, procs=8):
+    """One workload on this rank's GPU: device-resident leg, end-to-end leg, parity against the reference pin.
+    Returns the per-rank record (rank 0's record carries the whole-job numbers after the max-over-ranks)."""
     import torch
     import torch.distributed as dist
 
     from phyml_b200.engine import Engine, pack_ops
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    tree, m, pat, codes, desc = make_workload(args.workload, rank, world)
+    w = wl.WORKLOADS[name]
+    strong = w.n_blocks > 1
+    m, pin = wl.evaluation_model(name)
+    tree = wl.make_tree(w)
+    blocks = wl.rank_blocks(w, rank, world) if (strong or world > 1) else [0]
+    pat = wl.make_patterns(name, blocks, procs=min(procs, len(blocks)))
     ns, ncatg, P, n = m.ns, m.ncatg, pat.n_pattern, tree.n_otu
     eng = Engine(n, P, ns, ncatg, tree.n_clv_handles, tree.n_edges, device=local)
     if world > 1:
@@ -153,18 +167,22 @@ def run_b200(args):
         eng.set_weights_ptr(h_wght.data_ptr(), h_invar.data_ptr())
         eng.set_model(m)
 
+    k1_launches = [0]
+
     def evaluate(ev=None):
         eng.update_pmats(edges, lengths)                      # K0, all edges (lk.c:500-505)
         if ev is not None:
             ev[0].record(stream)
+        l0 = eng.launch_count
         eng.update_partials(ops_packed)                       # K1, post-order (lk.c:562)
         if ev is not None:
+            k1_launches[0] = eng.launch_count - l0            # device-resident leg only (the e2e leg adds the tip-row translation)
             ev[1].record(stream)
-        return eng.edge_lnl(left, rght, tree.root_edge)       # K2 (+ all-reduce when sharded)
+        return eng.edge_lnl(left, rght, tree.root_edge)       # K2 (+ cross-GPU sum when sharded)
 
     eng.set_tip_table(pat.table())
     upload_inputs()
-    lnl0 = evaluate()
+    evaluate()
 
     def barrier():
         if world > 1:
@@ -172,151 +190,234 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident leg: `value`
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         evaluate()
-    sampler = ClockSampler(local)
-    sampler.start()
-    t_wait = time.time()
-    while not sampler.rows and time.time() - t_wait < 15.0:   # nvidia-smi needs a moment to start
-        time.sleep(0.05)
-    k1_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler = None
+    if clocks:
+        sampler = ClockSampler(local)
+        sampler.start()
+        t_wait = time.time()
+        while not sampler.rows and time.time() - t_wait < 15.0:   # nvidia-smi needs a moment to start
+            time.sleep(0.05)
+    k1_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = eng.launch_count
     barrier()
-    sampler.mark()
+    if sampler:
+        sampler.mark()
     e0.record(stream)
-    for s in range(args.steps):
+    for s in range(steps):
         lnl = evaluate(k1_ev[s])
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count - launches0
     k1_ms = [a.elapsed_time(b) for a, b in k1_ev]
-    # keep the GPU under the same load until the sampler has seen it (its period is 100 ms, the timed leg ~10 ms);
-    # it is stopped before the e2e leg, whose many small driver calls an NVML poller would perturb
-    n_rows = len(sampler.rows)
-    t_wait = time.time()
-    while len(sampler.rows) < n_rows + 3 and time.time() - t_wait < 3.0:
-        # LOCAL work only (K0 + K1, no reduction): the number of iterations differs between ranks, so
-        # nothing in this loop may involve the cross-GPU exchange
-        eng.update_pmats(edges, lengths)
-        eng.update_partials(ops_packed)
-        eng.sync()
-    clocks = sampler.finish()
+    clk = None
+    if sampler:
+        # keep the GPU under the same load until the sampler has seen it (its period is 100 ms, the timed leg ~10 ms);
+        # it is stopped before the e2e leg, whose many small driver calls an NVML poller would perturb
+        n_rows = len(sampler.rows)
+        t_wait = time.time()
+        while len(sampler.rows) < n_rows + 3 and time.time() - t_wait < 3.0:
+            # LOCAL work only (K0 + K1, no reduction): the number of iterations differs between ranks, so
+            # nothing in this loop may involve the cross-GPU exchange
+            eng.update_pmats(edges, lengths)
+            eng.update_partials(ops_packed)
+            eng.sync()
+        clk = sampler.finish()
 
     # ---------------- end-to-end leg: host buffers in, lnL (+ per-site lnL) out, every step
-    for _ in range(max(1, args.warmup // 2)):
-        upload_inputs()
-        evaluate()
-        eng.get_site_lnl_ptr(h_site.data_ptr())
-    barrier()
-    t0 = time.perf_counter()
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g0.record(stream)
-    for s in range(args.steps):
-        upload_inputs()
-        lnl_e2e = evaluate()
-        eng.get_site_lnl_ptr(h_site.data_ptr())
-    g1.record(stream)
-    barrier()
-    e2e_ms = max(g0.elapsed_time(g1), (time.perf_counter() - t0) * 1e3)
-    assert abs(lnl_e2e - lnl) <= 1e-12 * abs(lnl)
-    assert abs(float(np.dot(h_site.numpy(), pat.wght)) - (lnl if world == 1 else float("nan"))) <= 1e-9 * abs(lnl) or world > 1
-
-    # max over ranks
-    if world > 1:
-        t = torch.tensor([ms, e2e_ms, float(P)], dtype=torch.float64, device="cuda")
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms, e2e_ms, P_total = float(tmax[0]), float(tmax[1]), float(tsum[2])
+    e2e_ms = None
+    lnl_e2e = lnl
+    if e2e:
+        for _ in range(max(1, warmup // 2)):
+            upload_inputs()
+            evaluate()
+            eng.get_site_lnl_ptr(h_site.data_ptr())
+        barrier()
+        t0 = time.perf_counter()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        for s in range(steps):
+            upload_inputs()
+            lnl_e2e = evaluate()
+            eng.get_site_lnl_ptr(h_site.data_ptr())
+        g1.record(stream)
+        barrier()
+        e2e_ms = max(g0.elapsed_time(g1), (time.perf_counter() - t0) * 1e3)
     else:
-        P_total = float(P)
+        eng.get_site_lnl_ptr(h_site.data_ptr())
+        eng.sync()
+    if abs(lnl_e2e - lnl) > 1e-12 * abs(lnl):
+        raise RuntimeError(f"e2e lnL {lnl_e2e!r} differs from the device-resident lnL {lnl!r}")
 
-    updates = P_total * (n - 2) * args.steps
-    value = updates / (ms * 1e-3)
-    e2e_value = updates / (e2e_ms * 1e-3)
+    # the exchange checked against an independent sum: this rank's partial (weights . per-pattern lnL on the host)
+    local_partial = float(np.dot(h_site.numpy(), pat.wght))
+    if world > 1:
+        t = torch.tensor([local_partial, float(P)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        host_sum, P_total = float(t[0]), float(t[1])
+        tm = torch.tensor([ms, e2e_ms or 0.0, statistics.mean(k1_ms)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ms, e2e_ms_max = float(tm[0]), float(tm[1])
+        e2e_ms = e2e_ms_max if e2e else None
+    else:
+        host_sum, P_total = local_partial, float(P)
+    exchange_rel_err = abs(host_sum - lnl) / abs(lnl)
+    if exchange_rel_err > 1e-11:
+        raise RuntimeError(f"all-rank lnL {lnl!r} differs from the sum of the per-rank partials {host_sum!r}")
+
+    lnl_ref = None
+    parity = None
+    if pin is not None and (strong or world == 1):
+        lnl_ref = float(pin["lnL"]) if (strong or w.n_blocks == 1) else None
+        if lnl_ref is not None:
+            parity = abs(lnl - lnl_ref) / abs(lnl_ref)
+            if parity > PARITY_RTOL:
+                raise RuntimeError(f"{name}: lnL {lnl!r} vs the reference's {lnl_ref!r}: relative error {parity:.3e} > {PARITY_RTOL}")
+
+    updates = P_total * (n - 2) * steps
+    k1_bytes = k1_algorithmic_bytes(tree, ops, P, ns, ncatg)
+    k1_avg_ms = statistics.mean(k1_ms)
     h2d = int(h_codes.numel() + h_wght.numel() * 8 + h_invar.numel() * 2 + (2 * ns * ns + 2 * ns + 2 * ncatg + 4) * 8
               + tree.n_edges * 16 + len(ops) * 28)
     d2h = int(P * 8 + 32)
+    rec = {
+        "name": name, "desc": w.desc, "strong": strong, "n_taxa": n, "ns": ns, "ncatg": ncatg, "P": P, "P_total": P_total,
+        "n_sites_total": w.block_sites * (w.n_blocks if strong else world), "blocks": blocks,
+        "ms": ms, "steps": steps, "value": updates / (ms * 1e-3), "launches": int(launches), "lnL": lnl,
+        "lnL_reference": lnl_ref, "parity_rel_err": parity, "exchange_rel_err": exchange_rel_err,
+        "e2e_ms": e2e_ms, "e2e_value": (updates / (e2e_ms * 1e-3)) if e2e_ms else None, "h2d": h2d, "d2h": d2h,
+        "k1_bytes": k1_bytes, "k1_ms": k1_avg_ms, "k1_launches": int(k1_launches[0]), "clocks": clk,
+        "updates_per_eval": n - 2, "device_bytes": eng.device_bytes, "tree": tree, "model": m, "ops": ops,
+    }
+    eng.close()
+    return rec
 
+
+def roofline_of(rec, peaks):
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = rec["k1_bytes"] / (rec["k1_ms"] * 1e-3) / 1e9
+    out = {"bound": "hbm", "kernel": k1_kernel_name(rec["ns"], rec["ncatg"]), "achieved": achieved, "peak": peak,
+           "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+           "unit": "GB/s", "frac": achieved / peak, "traffic": None, "traffic_source": None,
+           "algorithmic_bytes_per_eval": rec["k1_bytes"], "k1_ms_per_eval": rec["k1_ms"],
+           "k1_launches_per_eval": rec["k1_launches"]}
+    if rec["ns"] == 20:
+        # the 20-state path is the dense contraction on the FP64 tensor pipe: also report its flop rate
+        n_int = sum((0 if o.c1.is_tip else 1) + (0 if o.c2.is_tip else 1) for o in rec["ops"])
+        flops = 2.0 * 20 * 20 * rec["ncatg"] * rec["P"] * n_int            # useful MACs*2 of the P.x products
+        out["fp64_tensor"] = {"achieved_tflops": flops / (rec["k1_ms"] * 1e-3) / 1e12, "nominal_peak_tflops": 40.0,
+                              "note": "useful flops of the (20x20).(20xsites) contractions; MMA tiles are padded 20->24"}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        try:
+            t = json.load(open(tr))
+            out["traffic"] = t.get(rec["name"])
+            if out["traffic"] is not None:
+                out["traffic_source"] = t.get("_source", "profiles/ (ncu --set full capture of this command, dram read + write per K1 launch; static, not re-measured in this run)")
+        except Exception:
+            pass
+    return out
+
+
+def secondary_of(rec, peaks):
+    rf = roofline_of(rec, peaks)
+    return {"workload": rec["desc"], "name": rec["name"], "patterns": rec["P"], "n_taxa": rec["n_taxa"],
+            "value": rec["value"], "unit": UNIT, "ms_per_step": rec["ms"] / rec["steps"], "steps": rec["steps"],
+            "lnL": rec["lnL"], "lnL_reference": rec["lnL_reference"], "parity_rel_err": rec["parity_rel_err"],
+            "gpu_launches": rec["launches"], "device_gb": rec["device_bytes"] / 1e9,
+            "e2e": None if rec["e2e_value"] is None else {"value": rec["e2e_value"], "unit": UNIT,
+                                                          "ms_per_step": rec["e2e_ms"] / rec["steps"],
+                                                          "h2d_bytes_per_step": rec["h2d"], "d2h_bytes_per_step": rec["d2h"]},
+            "roofline": rf}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    name = args.workload or default_workload(world)
+    rec = measure(name, rank, world, local, args.steps, args.warmup)
     out = None
     if rank == 0:
-        peaks = {}
-        pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(pk_path):
-            peaks = json.load(open(pk_path))
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        k1_bytes = k1_algorithmic_bytes(tree, ops, P, ns, ncatg)
-        k1_avg_ms = statistics.mean(k1_ms)
-        achieved = k1_bytes / (k1_avg_ms * 1e-3) / 1e9
+        peaks = load_peaks()
+        w = wl.WORKLOADS[name]
         out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "name": args.workload, "n_taxa": n, "sites_per_gpu": WORKLOADS[args.workload][2],
-                       "patterns_per_gpu": P, "ns": ns, "ncatg": ncatg, "updates_per_eval": n - 2,
-                       "parallelism": f"site-shard x{world}", "both_sides": False,
+            "metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": rec["ms"] / args.steps, "higher_is_better": True,
+            "scaling": "strong" if rec["strong"] else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": rec["desc"], "name": name, "n_taxa": rec["n_taxa"], "sites_total": rec["n_sites_total"],
+                       "patterns_total": int(rec["P_total"]), "patterns_rank0": rec["P"], "ns": rec["ns"], "ncatg": rec["ncatg"],
+                       "updates_per_eval": rec["updates_per_eval"], "parallelism": f"site-shard x{world}",
+                       "column_blocks_per_rank": len(rec["blocks"]), "both_sides": False,
                        "exchange": ("none" if world == 1 else os.environ.get("PLK_COMM", "p2p")),
-                       "l2": "CLV working set %.2f GB per evaluation > 126 MB L2 (no flush needed)"
-                             % ((n - 2) * P * ns * ncatg * 8 / 1e9)},
-            "evals_per_s": args.steps / (ms * 1e-3), "lnL": lnl,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_traverse_dna<4,2>" if ns == 4 else ("k_traverse_aa (DMMA.8x8x4)" if ns == 20 else "k_partial_generic"),
-                         "achieved": achieved, "peak": peak,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "algorithmic_bytes_per_eval": k1_bytes, "k1_ms_per_eval": k1_avg_ms,
-                         "k1_launches_per_eval": None},
+                       "model": "the reference's eigen system for `%s` (tests/golden/big/%s.npz)" % (" ".join(wl.REF_ARGS[w.ns]), name),
+                       "l2": "CLV working set %.2f GB per evaluation and GPU > 126 MB L2 (no flush needed)"
+                             % ((rec["n_taxa"] - 2) * rec["P"] * rec["ns"] * rec["ncatg"] * 8 / 1e9)},
+            "evals_per_s": args.steps / (rec["ms"] * 1e-3), "lnL": rec["lnL"], "lnL_reference": rec["lnL_reference"],
+            "parity_rel_err": rec["parity_rel_err"], "parity_rtol": PARITY_RTOL,
+            "exchange_rel_err": rec["exchange_rel_err"],
+            "e2e": {"value": rec["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": rec["h2d"], "d2h_bytes_per_step": rec["d2h"],
+                    "ms_per_step": rec["e2e_ms"] / args.steps},
+            "gpu_launches": rec["launches"],
+            "clocks": rec["clocks"],
+            "roofline": roofline_of(rec, peaks),
         }
-        if ns == 20:
-            # the 20-state path is the dense contraction on the FP64 tensor pipe: also report its flop rate
-            n_int = sum((0 if o.c1.is_tip else 1) + (0 if o.c2.is_tip else 1) for o in ops)
-            flops = 2.0 * 20 * 20 * ncatg * P * n_int            # useful MACs*2 of the P.x products
-            out["roofline"]["fp64_tensor"] = {"achieved_tflops": flops / (k1_avg_ms * 1e-3) / 1e12,
-                                              "nominal_peak_tflops": 40.0,
-                                              "note": "useful flops of the (20x20).(20xsites) contractions; MMA tiles are padded 20->24"}
-        tr = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tr):
-            try:
-                out["roofline"]["traffic"] = json.load(open(tr)).get(args.workload)
-            except Exception:
-                pass
-        if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(tree, codes, m, cores=1, sites=args.cpu_sites, evals=args.cpu_evals)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    eng.close()
+    if rank == 0 and world == 1:
+        if not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(name, cores=1, sites=args.cpu_sites, evals=args.cpu_evals, gpu_check=local)
+        if not args.no_secondary and name == "dna_100x100k":
+            sec = {}
+            for nm, st in (("aa_200x50k", min(args.steps, 10)), ("dna_500x1M", min(args.steps, 5))):
+                try:
+                    r2 = measure(nm, 0, 1, local, st, 3, e2e=(nm == "aa_200x50k"), clocks=False, procs=16)
+                    sec[nm] = secondary_of(r2, peaks)
+                except Exception as ex:  # a secondary workload must never take the headline line down
+                    sec[nm] = {"error": f"{type(ex).__name__}: {ex}"}
+            out["secondary"] = sec
     if rank == 0:
         print(json.dumps(out))
 
 
 # ======================================================================================================
-def cpu_baseline(tree, codes, m, cores, sites, evals, warm=1):
+def cpu_baseline(name, cores, sites, evals, warm=1, gpu_check=None, seed_block=0):
     """Times the reference's own Lk(NULL) (oracle/_ref/ref_driver = the unmodified reference built
     from /root/reference sources, AVX2+FMA path) on `cores` processes, each on its own slice of
-    columns (the reference is single-threaded).  Falls back to the C oracle port if _ref is absent."""
+    columns of the workload's first block(s) (the reference is single-threaded).  Falls back to the C
+    oracle port if _ref is absent.  With `gpu_check` (a device index) the engine evaluates the SAME
+    column sample and the relative difference of the two lnL is reported."""
+    w = wl.WORKLOADS[name]
+    tree = wl.make_tree(w)
     n = tree.n_otu
     driver = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    codes = wl.block_codes(w, seed_block)
+    while codes.shape[1] < sites and w.n_blocks > 1 and seed_block + 1 < w.n_blocks:
+        seed_block += 1
+        codes = np.concatenate([codes, wl.block_codes(w, seed_block)], axis=1)
     sites = min(sites, codes.shape[1])
+    per = sites // cores
     if os.path.exists(driver):
         with tempfile.TemporaryDirectory() as wd:
             with open(os.path.join(wd, "tree.nwk"), "w") as f:
                 f.write(tree.to_newick() + "\n")
             procs = []
-            per = sites // cores
             for c in range(cores):
                 phy = os.path.join(wd, f"aln{c}.phy")
-                alignment.write_phylip(phy, codes[:, c * per:(c + 1) * per], m.ns, tree.names)
-                dt = ["-d", "nt", "-m", "GTR"] if m.ns == 4 else ["-d", "aa", "-m", "LG"]
+                alignment.write_phylip(phy, codes[:, c * per:(c + 1) * per], w.ns, tree.names)
                 cmd = [driver, "--time", str(evals), "--warmup", str(warm), "--", "-i", phy, "-u",
-                       os.path.join(wd, "tree.nwk")] + dt + ["-c", "4", "-a", "0.5", "-f", "e" if m.ns == 4 else "m",
-                                                              "-o", "n", "-b", "0", "--r_seed", "1", "--no_memory_check"]
+                       os.path.join(wd, "tree.nwk")] + wl.REF_ARGS[w.ns] + ["-o", "n", "-b", "0", "--r_seed", "1", "--no_memory_check"]
                 procs.append(subprocess.Popen(cmd, cwd=wd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True))
             res = []
             for p in procs:
@@ -327,17 +428,31 @@ def cpu_baseline(tree, codes, m, cores, sites, evals, warm=1):
                 res.append(json.loads(line[0][len("REF_TIMING "):]))
         slowest = max(r["mean_s"] for r in res)
         pats = sum(r["n_pattern"] for r in res)
-        return {"value": pats * (n - 2) / slowest, "unit": UNIT, "cores": cores, "kind": "reference",
-                "sample": f"{n} taxa x {per * cores} sites ({pats} patterns), {evals} timed Lk(NULL) per process after "
-                          f"{warm} warm-up, {cores} process(es) x 1 thread, gcc -O3 -march=haswell (AVX2+FMA kernels)",
-                "s_per_eval": slowest, "lnL_sample": [r["lnL"] for r in res]}
+        out = {"value": pats * (n - 2) / slowest, "unit": UNIT, "cores": cores, "kind": "reference",
+               "sample": f"{n} taxa x {per * cores} sites ({pats} patterns; the first columns of the benchmarked alignment), "
+                         f"{evals} timed Lk(NULL) per process after {warm} warm-up, {cores} process(es) x 1 thread, "
+                         f"gcc -O3 -march=haswell (AVX2+FMA kernels)",
+               "s_per_eval": slowest, "lnL_sample": [r["lnL"] for r in res]}
+        if gpu_check is not None and cores == 1:
+            from phyml_b200.engine import Engine
+            from phyml_b200.lk import LkTree
+
+            m, _ = wl.evaluation_model(name)
+            pat = alignment.compress(codes[:, :per], w.ns)
+            t = LkTree(tree, pat, m, Engine(n, pat.n_pattern, w.ns, m.ncatg, tree.n_clv_handles, tree.n_edges, device=gpu_check))
+            g = t.Lk()
+            t.eng.close()
+            out["lnL_sample_gpu"] = g
+            out["sample_parity_rel_err"] = abs(g - res[0]["lnL"]) / abs(res[0]["lnL"])
+        return out
     # port: C oracle through the test backend
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle_backend import OracleBackend
     from phyml_b200.lk import LkTree
 
+    m, _ = wl.evaluation_model(name)
     sites = min(sites, 5000)
-    pat = alignment.compress(codes[:, :sites], m.ns)
+    pat = alignment.compress(codes[:, :sites], w.ns)
     t = LkTree(tree, pat, m, OracleBackend(n, pat.n_pattern, m.ns, m.ncatg, tree.n_clv_handles, tree.n_edges))
     t.Lk()
     t0 = time.perf_counter()
@@ -352,24 +467,28 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ns, n_taxa, sites, desc = WORKLOADS[args.workload]
-    tree = Tree.random(n_taxa, seed=1)
-    m = pmodel.gtr(alpha=0.5) if ns == 4 else pmodel.lg_from_fixture(alpha=0.5)
+    name = args.workload or default_workload(args.gpus)
+    w = wl.WORKLOADS[name]
     cores = os.cpu_count() or 1
     # bounded sample: every host core gets its own block of columns of the workload's shape (sites are
     # independent, the reference is single-threaded: one process per core).  1 000 columns per core keeps a
     # process's likelihood arena near 38 MB: measured on the 128-core GPU-box host this is the reference's
     # best case (2.2e8 updates/s; 3 000 columns per core drop to 1.6e8, memory-bandwidth bound)
-    per_core = 1000 if ns == 4 else 200
-    budget = int(1.5e7 * 90 / max(1, (args.steps + args.warmup)) / (n_taxa - 2))   # ~90 s at 1.5e7 updates/s/core
-    per_core = max(200, min(per_core, budget))
-    codes = alignment.simulate(tree, m, per_core * cores, seed=1000)
-    cb = cpu_baseline(tree, codes, m, cores=cores, sites=per_core * cores, evals=args.steps, warm=args.warmup)
+    per_core = 1000 if w.ns == 4 else 200
+    budget = int(1.5e7 * 90 / max(1, (args.steps + args.warmup)) / (w.n_taxa - 2))   # ~90 s at 1.5e7 updates/s/core
+    per_core = max(100, min(per_core, budget))
+    total = w.block_sites * w.n_blocks
+    if per_core * cores > total:
+        per_core = max(50, total // cores)
+        cores = max(1, min(cores, total // per_core))
+    cb = cpu_baseline(name, cores=cores, sites=per_core * cores, evals=args.steps, warm=args.warmup)
     out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["s_per_eval"] * 1e3,
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": desc, "name": args.workload, "n_taxa": n_taxa, "ns": ns, "ncatg": 4,
-                      "note": "reference CPU implementation (host cores); each step = one Lk(NULL) on a bounded column sample"},
+           "higher_is_better": True, "scaling": "strong" if w.n_blocks > 1 else "weak", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic",
+           "config": {"workload": w.desc, "name": name, "n_taxa": w.n_taxa, "ns": w.ns, "ncatg": 4,
+                      "note": "reference CPU implementation (host cores); each step = one Lk(NULL) on a bounded column sample "
+                              "of the workload's alignment (its first columns, one slice per core)"},
            "cpu_baseline": cb,
            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
@@ -381,8 +500,10 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="dna_100x100k", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=list(wl.WORKLOADS),
+                    help="default: dna_100x100k on 1 GPU (BASELINE configs[1]), dna_500x1M on N>1 (configs[3], strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--cpu-sites", type=int, default=25_000)
     ap.add_argument("--cpu-evals", type=int, default=40)
     args = ap.parse_args()

@@ -129,7 +129,7 @@ struct plk_instance
   int    trav_umax = 2;                // items per thread of the fused traversal kernel
   int    trav_blocks_per_sm = 2;
   int    trav_v1 = 0;            // PLK_TRAV_V1=1: first-generation kernel (k_traverse_dna), kept for A/B measurements
-  int    t2_variant = 0;         // PLK_T2_VARIANT: (compute warps, blocks/SM) of k_traverse_dna2
+  int    t2_variant = 11;        // PLK_T2_VARIANT: < 10: k_traverse_dna2, >= 10: k_traverse_dna3 (compute warps, blocks/SM)
   bool   aa_attr_set = false;
   int    blocked = 0;            // CLVs in the blocked layout (ns = 4, 20), see clv_off()
   int    dna_mma = 0;            // use k_traverse_dna_mma (tensor-pipe variant) for ns = 4
@@ -189,7 +189,7 @@ inline int use_device(plk_instance *inst)
     if (rc_) return rc_;          \
   } while (0)
 
-// run `call` (an expression using `sh`, the shard, and `lo`/`n`, its pattern block) on every shard
+// run `call` (an expression using `sh`, the shard, and `lo`, the first pattern of its block) on every shard
 #define FOR_SHARDS(inst, call)                                                   \
   do                                                                             \
   {                                                                              \
@@ -197,9 +197,7 @@ inline int use_device(plk_instance *inst)
     {                                                                            \
       plk_instance *sh = (inst)->shards[i_];                                     \
       const size_t  lo = (size_t)(inst)->shard_lo[i_];                           \
-      const size_t  n = (size_t)((inst)->shard_lo[i_ + 1] - (inst)->shard_lo[i_]); \
       (void)lo;                                                                  \
-      (void)n;                                                                   \
       int rc_ = (call);                                                          \
       if (rc_)                                                                   \
       {                                                                          \
@@ -1024,15 +1022,14 @@ static int launch_traverse3_t(plk_instance *inst, const OpDev *d_ops, int n_ops)
   int              cap = (int)((budget - t3_smem_bytes<NCATG>(0)) / t3_chunk_bytes<NCATG>());
   cap = std::min(std::min(cap, 32 * W), kT3MaxTileChunks) & ~1;  // live mask: 32 bits per warp; staged tip rows
   const int       slots = inst->num_sms * MINB;
-  const long long per_round = (long long)slots * cap;
-  const int       rounds = (int)((total_chunks + per_round - 1) / per_round);
-  int             n_tiles = std::max(1, std::min(slots * rounds, total_chunks));
-  int             tile_chunks = (total_chunks + n_tiles - 1) / n_tiles;
-  tile_chunks = std::min((tile_chunks + 1) & ~1, cap);  // even: the TMA copies of the tip rows start on 16 bytes
-  n_tiles = (total_chunks + tile_chunks - 1) / tile_chunks;
-  const int     grid = std::min(n_tiles, slots);
-  const size_t  smem = t3_smem_bytes<NCATG>(tile_chunks);
-  auto          kern = k_traverse_dna3<NCATG, W, MINB>;
+  const int       pairs = (total_chunks + 1) / 2;  // tiles are whole pairs of chunks (t3_tile_range)
+  const long long per_round = (long long)slots * (cap / 2);
+  const int       rounds = (int)((pairs + per_round - 1) / per_round);
+  const int       n_tiles = (int)std::max<long long>(1, std::min<long long>((long long)slots * rounds, pairs));
+  const int       tile_chunks = 2 * ((pairs + n_tiles - 1) / n_tiles);  // the largest tile
+  const int       grid = std::min(n_tiles, slots);
+  const size_t    smem = t3_smem_bytes<NCATG>(tile_chunks);
+  auto            kern = k_traverse_dna3<NCATG, W, MINB>;
   static size_t smem_set[64] = {};  // per instantiation and device
   if (smem_set[inst->cfg.device & 63] == 0)
   {

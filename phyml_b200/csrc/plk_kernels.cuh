@@ -1520,6 +1520,18 @@ __device__ __forceinline__ void t3_run_op(const T3Stage<NCATG> &stg, uint32_t fw
 }
 #undef T3_LOAD
 
+// tile -> chunk range.  Tiles are whole PAIRS of chunks (the TMA copies of the staged tip rows start on 16 bytes)
+// and differ by at most one pair, so that every block of the persistent grid has work (148 tiles of 66 or 68
+// chunks instead of 145 tiles of 68 for 9 811 chunks).
+__device__ __forceinline__ void t3_tile_range(int tile, int total_chunks, int n_tiles, int &chunk0, int &n_chunks)
+{
+  const int pairs = (total_chunks + 1) >> 1;
+  const int base = pairs / n_tiles, rem = pairs - base * n_tiles;
+  const int p0 = tile * base + min(tile, rem);
+  chunk0 = 2 * p0;
+  n_chunks = min(2 * (base + (tile < rem ? 1 : 0)), total_chunks - chunk0);
+}
+
 template <int NCATG, int W, int MINB>
 __global__ void __launch_bounds__((W + 1) * 32, MINB)
     k_traverse_dna3(const OpDev *__restrict__ ops, int n_ops, int total_chunks, int tile_chunks, int n_tiles,
@@ -1572,9 +1584,10 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB)
           const int       s = (int)(it % S);
           const uint32_t  ph = (uint32_t)((it / S) & 1);
           const int       tile = (int)blockIdx.x + (int)(it / n_ops) * (int)gridDim.x;
-          const int       chunk0 = tile * tile_chunks;
+          int             chunk0, tile_n;
+          t3_tile_range(tile, total_chunks, n_tiles, chunk0, tile_n);
           // tip rows of the tile: whole 16-byte units (tiles start on even chunks, rows are padded)
-          const uint32_t rb = (uint32_t)((min(tile_chunks, total_chunks - chunk0) * 8 + 15) & ~15);
+          const uint32_t rb = (uint32_t)((tile_n * 8 + 15) & ~15);
           const bool     tipA = (kind & 3) == kSrcTip, tipB = (kind >> 2) == kSrcTip;
           mbar_wait_backoff(&empty[s], ph ^ 1u);
           const uint32_t b1 = tipA ? TB : PB;
@@ -1597,8 +1610,8 @@ __global__ void __launch_bounds__((W + 1) * 32, MINB)
   for (int r = 0; r < rounds; ++r)
   {
     const int tile = (int)blockIdx.x + r * (int)gridDim.x;
-    const int chunk0 = tile * tile_chunks;
-    const int n_chunks = min(tile_chunks, total_chunks - chunk0);
+    int       chunk0, n_chunks;
+    t3_tile_range(tile, total_chunks, n_tiles, chunk0, n_chunks);
     const int nch = (n_chunks > warp) ? (n_chunks - 1 - warp) / W + 1 : 0;  // chunks warp, warp + W, ... of the tile
     const int sidx0 = (chunk0 + warp) * 8 + (lane >> 2);
     const int goff0 = (chunk0 + warp) * NCATG * 32 + lane;  // blocked layout, < 2^31 doubles

@@ -78,6 +78,8 @@ def test_sharded_instance_on_one_device_matches_reference():
     assert abs(lnl1 - lnl) <= 1e-12 * abs(lnl)
     e = 11
     for x in (t, t1):
+        x.Set_Both_Sides(1)
+        x.Lk()
         x.Set_Update_Eigen_Lr(1)
         x.Lk(e)
         x.Set_Update_Eigen_Lr(0)
