@@ -131,6 +131,14 @@ int plk_update_partials(plk_instance *inst, int n_ops, const plk_op *ops);
 int plk_edge_lnl(plk_instance *inst, plk_side left, plk_side rght, int pmat, double *lnl,
                  int *numerical_warning);
 
+/* ---- K1 + K2: a traversal and the edge reduction in one call --------------------------------
+ * replaces the body of Lk(NULL) after the P-matrix loop: Post_Order_Lk (src/lk.c:562-564) followed by
+ * the site loop at the root edge (src/lk.c:578-645).  Same results and by-products as
+ * plk_update_partials + plk_edge_lnl; for 4-state data with 4 rate categories the edge reduction
+ * runs as the epilogue of the traversal kernel (one launch per full-tree evaluation). */
+int plk_traverse_edge_lnl(plk_instance *inst, int n_ops, const plk_op *ops, plk_side left,
+                          plk_side rght, int pmat, double *lnl, int *numerical_warning);
+
 /* ---- K3: eigen-basis projection -------------------------------------------------------------
  * replaces Update_Eigen_Lr (src/lk.c:1038-1114, src/avx.c:21-105): tree->dot_prod stays on the
  * device; also latches fact_sum_scale = scale(left)+scale(rght) for K4. */

@@ -574,6 +574,21 @@ phydbl Lk(t_edge *b, t_tree *tree)
 
   tree->c_lnL = .0;
   tree->sum_min_sum_scale = .0;
+  if (tree->update_eigen_lr == NO && tree->use_eigen_lr == NO && sh->n_queue > 0)
+  { /* the queued CLV updates and the site loop at b as ONE engine call: a full traversal (Lk(NULL)) or the one to
+       three updates of an SPR / NNI candidate followed by Lk(b) become a single launch (lk.c:562-645) */
+    if (sh->n_pm_queue > 0)
+    {
+      CK(plk_update_pmats(sh->inst, sh->n_pm_queue, sh->pm_h, sh->pm_l), sh);
+      sh->n_pm_queue = 0;
+    }
+    CK(plk_traverse_edge_lnl(sh->inst, sh->n_queue, sh->queue, side_of(sh, b->left, b->p_lk_left),
+                             side_of(sh, b->rght, b->p_lk_rght), pm_handle(sh, b->Pij_rr), &lnl, &warn),
+       sh);
+    sh->n_queue = 0;
+    sh->n_flush++;
+    goto have_lnl;
+  }
   flush(sh);
   if (tree->update_eigen_lr == YES) Update_Eigen_Lr(b, tree); /* lk.c:590 */
   if (tree->use_eigen_lr == YES)
@@ -582,6 +597,7 @@ phydbl Lk(t_edge *b, t_tree *tree)
     CK(plk_edge_lnl(sh->inst, side_of(sh, b->left, b->p_lk_left), side_of(sh, b->rght, b->p_lk_rght),
                     pm_handle(sh, b->Pij_rr), &lnl, &warn),
        sh);
+have_lnl:
   tree->c_lnL = lnl;
   if (warn) tree->numerical_warning = YES;
   if (full && !getenv("PLK_SHIM_NO_SITE_READBACK"))

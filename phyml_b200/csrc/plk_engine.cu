@@ -129,7 +129,11 @@ struct plk_instance
   int    trav_umax = 2;                // items per thread of the fused traversal kernel
   int    trav_blocks_per_sm = 2;
   int    trav_v1 = 0;            // PLK_TRAV_V1=1: first-generation kernel (k_traverse_dna), kept for A/B measurements
-  int    t2_variant = 11;        // PLK_T2_VARIANT: < 10: k_traverse_dna2, >= 10: k_traverse_dna3 (compute warps, blocks/SM)
+  // Post_Order_Lk + edge reduction in one launch (plk_traverse_edge_lnl): request consumed by launch_traverse4_t
+  bool     pending_edge = false, edge_fused = false;
+  plk_side edge_left{}, edge_rght{};
+  int      edge_pmat = 0;
+  int    t2_variant = 20;        // PLK_T2_VARIANT: < 10: k_traverse_dna2, 10..19: k_traverse_dna3, >= 20: k_traverse_dna4 (default)
   bool   aa_attr_set = false;
   int    blocked = 0;            // CLVs in the blocked layout (ns = 4, 20), see clv_off()
   int    dna_mma = 0;            // use k_traverse_dna_mma (tensor-pipe variant) for ns = 4
@@ -1003,10 +1007,6 @@ static int launch_traverse2_nc(plk_instance *inst, const OpDev *d_ops, int n_ops
   constexpr int kW1 = (NCATG == 8) ? 10 : 11;  // 8 categories: a chunk is half an 8-site block, W must be even
   switch (inst->t2_variant)
   {
-  case 1: return launch_traverse2_t<NCATG, 6, 2>(inst, d_ops, n_ops);
-  case 2: return launch_traverse2_t<NCATG, 12, 1>(inst, d_ops, n_ops);
-  case 3: return launch_traverse2_t<NCATG, 10, 1>(inst, d_ops, n_ops);
-  case 4: return launch_traverse2_t<NCATG, 14, 1>(inst, d_ops, n_ops);
   case 5: return launch_traverse2_t<NCATG, (NCATG == 8) ? 4 : 5, 2>(inst, d_ops, n_ops);
   default: return launch_traverse2_t<NCATG, kW1, 1>(inst, d_ops, n_ops);
   }
@@ -1048,12 +1048,8 @@ static int launch_traverse3_nc(plk_instance *inst, const OpDev *d_ops, int n_ops
 {
   switch (inst->t2_variant)
   {
-  case 11: return launch_traverse3_t<NCATG, 15, 1>(inst, d_ops, n_ops);
-  case 12: return launch_traverse3_t<NCATG, 31, 1>(inst, d_ops, n_ops);
   case 13: return launch_traverse3_t<NCATG, 7, 2>(inst, d_ops, n_ops);
-  case 14: return launch_traverse3_t<NCATG, 7, 3>(inst, d_ops, n_ops);
-  case 15: return launch_traverse3_t<NCATG, 11, 2>(inst, d_ops, n_ops);
-  default: return launch_traverse3_t<NCATG, 23, 1>(inst, d_ops, n_ops);
+  default: return launch_traverse3_t<NCATG, 15, 1>(inst, d_ops, n_ops);
   }
 }
 
@@ -1065,6 +1061,97 @@ static int launch_traverse3(plk_instance *inst, const OpDev *d_ops, int n_ops)
   case 2: return launch_traverse3_nc<2>(inst, d_ops, n_ops);
   case 4: return launch_traverse3_nc<4>(inst, d_ops, n_ops);
   case 8: return launch_traverse3_nc<8>(inst, d_ops, n_ops);
+  }
+  inst->err = "internal: unsupported ncatg for traversal kernel";
+  return PLK_ERR_ARG;
+}
+
+// argument block of the 4-state edge reduction (stand-alone kernel or fused epilogue of the traversal kernel);
+// takes the next reduction sequence number
+static EdgeDev make_edge_dev(plk_instance *inst, plk_side left, plk_side rght, int pmat)
+{
+  EdgeDev e;
+  e.left = side_dev(inst, left);
+  e.rght = side_dev(inst, rght);
+  e.P = inst->d_pmat + (size_t)pmat * inst->pmat_stride;
+  e.mod = inst->d_model;
+  e.wght = inst->d_wght;
+  e.invar = inst->d_invar;
+  e.tipmask = inst->d_tipmask;
+  e.site_lnl = inst->d_site_lnl;
+  e.site_lk_out = inst->d_site_lk;
+  e.site_lk_cat = inst->d_site_lk_cat;
+  e.fact_sum_scale = inst->d_fact;
+  e.npat = inst->cfg.n_patterns;
+  e.enabled = 1;
+  e.ro = make_reduce_out(inst);
+  return e;
+}
+
+// op-major tensor-pipe 4-state traversal, round-robin items (k_traverse_dna4): chunks of two 8-site blocks
+template <int NCATG, int W>
+static int launch_traverse4_t(plk_instance *inst, const OpDev *d_ops, int n_ops)
+{
+  constexpr size_t kSmemPerSm = 227 * 1024;
+  const int        total_chunks = (inst->cfg.n_patterns + 15) / 16;
+  const size_t     budget = kSmemPerSm - 4096;  // static shared memory: barriers + the reduction scratch of the fused epilogue
+  int              cap = (int)((budget - t4_smem_bytes<NCATG>(0)) / (t4_smem_bytes<NCATG>(1) - t4_smem_bytes<NCATG>(0)));
+  cap = std::min(cap, kT4MaxTileChunks);
+  const int       slots = inst->num_sms;
+  const long long per_round = (long long)slots * cap;
+  const int       rounds = (int)((total_chunks + per_round - 1) / per_round);
+  const int       n_tiles = (int)std::max<long long>(1, std::min<long long>((long long)slots * rounds, total_chunks));
+  const int       tile_chunks = (total_chunks + n_tiles - 1) / n_tiles;  // the largest tile
+  const int       grid = std::min(n_tiles, slots);
+  const size_t    smem = t4_smem_bytes<NCATG>(tile_chunks);
+  auto            kern = k_traverse_dna4<NCATG, W>;
+  static size_t   smem_set[64] = {};  // per instantiation and device
+  if (smem_set[inst->cfg.device & 63] == 0)
+  {
+    CU_TRY(inst, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(budget)));
+    smem_set[inst->cfg.device & 63] = budget;
+  }
+  EdgeDev edge;
+  memset(&edge, 0, sizeof(edge));
+  if (inst->pending_edge && NCATG == 4)
+  {  // the edge reduction rides on this launch (its operands exist now: every destination has been allocated)
+    int rc = check_side(inst, inst->edge_left, true);
+    if (rc) return rc;
+    rc = check_side(inst, inst->edge_rght, true);
+    if (rc) return rc;
+    ARG_CHECK(inst, inst->edge_pmat >= 0 && inst->edge_pmat < inst->cfg.n_pmat, "plk_traverse_edge_lnl: bad arguments");
+    edge = make_edge_dev(inst, inst->edge_left, inst->edge_rght, inst->edge_pmat);
+    inst->edge_fused = true;
+    inst->pending_edge = false;
+  }
+  kern<<<grid, (W + 1) * 32, smem, inst->stream>>>(d_ops, n_ops, total_chunks, tile_chunks, n_tiles, inst->d_wght,
+                                                    inst->apply_scaling, edge);
+  inst->launches++;
+  CU_TRY(inst, cudaGetLastError());
+  return PLK_OK;
+}
+
+template <int NCATG>
+static int launch_traverse4_nc(plk_instance *inst, const OpDev *d_ops, int n_ops)
+{
+  switch (inst->t2_variant)
+  {
+  case 21: return launch_traverse4_t<NCATG, 17>(inst, d_ops, n_ops);
+  case 22: return launch_traverse4_t<NCATG, 19>(inst, d_ops, n_ops);
+  case 23: return launch_traverse4_t<NCATG, 13>(inst, d_ops, n_ops);
+  case 24: return launch_traverse4_t<NCATG, 11>(inst, d_ops, n_ops);
+  default: return launch_traverse4_t<NCATG, 15>(inst, d_ops, n_ops);
+  }
+}
+
+static int launch_traverse4(plk_instance *inst, const OpDev *d_ops, int n_ops)
+{
+  switch (inst->cfg.ncatg)
+  {
+  case 1: return launch_traverse4_nc<1>(inst, d_ops, n_ops);
+  case 2: return launch_traverse4_nc<2>(inst, d_ops, n_ops);
+  case 4: return launch_traverse4_nc<4>(inst, d_ops, n_ops);
+  case 8: return launch_traverse4_nc<8>(inst, d_ops, n_ops);
   }
   inst->err = "internal: unsupported ncatg for traversal kernel";
   return PLK_ERR_ARG;
@@ -1116,6 +1203,7 @@ int plk_update_partials(plk_instance *inst, int n_ops, const plk_op *ops)
   auto launch_fused = [&](const OpDev *d_ops, int n) {
     return (fused_dna && inst->dna_mma && nc <= 4) ? launch_traverse_mma(inst, d_ops, n)
            : (fused_dna && inst->trav_v1)          ? launch_traverse(inst, d_ops, n)
+           : (fused_dna && inst->t2_variant >= 20) ? launch_traverse4(inst, d_ops, n)
            : (fused_dna && inst->t2_variant >= 10) ? launch_traverse3(inst, d_ops, n)
            : fused_dna                             ? launch_traverse2(inst, d_ops, n)
                                                    : launch_traverse_aa(inst, d_ops, n);
@@ -1314,11 +1402,7 @@ static int edge_lnl_launch(plk_instance *inst, plk_side left, plk_side rght, int
   {  // coalesced 4-state kernel on the blocked layout: thread per (site, category)
     const int groups = (inst->cfg.n_patterns + 7) / 8;
     const int grid = std::max(1, std::min((groups + 3) / 4, std::min(kMaxReduceBlocks, inst->num_sms * 16)));
-    k_edge_lnl_dna<4><<<grid, 128, 0, inst->stream>>>(side_dev(inst, left), side_dev(inst, rght),
-                                                      inst->d_pmat + (size_t)pmat * inst->pmat_stride, inst->d_model,
-                                                      inst->cfg.n_patterns, inst->d_wght, inst->d_invar, inst->d_tipmask,
-                                                      inst->d_site_lnl, inst->d_site_lk, inst->d_site_lk_cat,
-                                                      inst->d_fact, make_reduce_out(inst));
+    k_edge_lnl_dna<4><<<grid, 128, 0, inst->stream>>>(make_edge_dev(inst, left, rght, pmat));
   }
   else
   {
@@ -1344,6 +1428,50 @@ int plk_edge_lnl(plk_instance *inst, plk_side left, plk_side rght, int pmat, dou
     return finish_sharded(inst, lnl, nullptr, warn);
   }
   const int rc = edge_lnl_launch(inst, left, rght, pmat);
+  if (rc) return rc;
+  return finish_reduction(inst, lnl, nullptr, warn);
+}
+
+// ---- K1 + K2 in one launch ------------------------------------------------------------------------
+// Post_Order_Lk followed by the site loop of Lk at one edge (lk.c:562-645).  When the whole list is one launch of
+// the 4-state traversal kernel the edge reduction runs as that kernel's epilogue; otherwise the two launches follow
+// each other on the stream.  Same results as plk_update_partials + plk_edge_lnl up to the summation order of
+// the per-block partial sums (the reduction stays deterministic: fixed partition, fixed order).
+static int traverse_edge_launch(plk_instance *inst, int n_ops, const plk_op *ops, plk_side left, plk_side rght, int pmat)
+{
+  static const bool disabled = getenv("PLK_NO_FUSED_EDGE") != nullptr;
+  const int         per_slot = (int)(kStageBytes / sizeof(OpDev));
+  const bool        can_fuse = !disabled && inst->fused_dna && inst->cfg.ncatg == 4 && inst->t2_variant >= 20 &&
+                        !inst->trav_v1 && !inst->dna_mma && n_ops > 0 && n_ops <= per_slot;
+  inst->edge_fused = false;
+  if (can_fuse)
+  {
+    inst->edge_left = left;
+    inst->edge_rght = rght;
+    inst->edge_pmat = pmat;
+    inst->pending_edge = true;
+  }
+  const int rc = plk_update_partials(inst, n_ops, ops);
+  inst->pending_edge = false;
+  if (rc) return rc;
+  if (inst->edge_fused)
+  {
+    inst->site_valid = true;
+    return PLK_OK;
+  }
+  return edge_lnl_launch(inst, left, rght, pmat);
+}
+
+int plk_traverse_edge_lnl(plk_instance *inst, int n_ops, const plk_op *ops, plk_side left, plk_side rght, int pmat,
+                          double *lnl, int *warn)
+{
+  ARG_CHECK(inst, lnl != nullptr && n_ops >= 0 && (n_ops == 0 || ops), "plk_traverse_edge_lnl: bad arguments");
+  if (!inst->shards.empty())
+  {
+    FOR_SHARDS(inst, traverse_edge_launch(sh, n_ops, ops, left, rght, pmat));
+    return finish_sharded(inst, lnl, nullptr, warn);
+  }
+  const int rc = traverse_edge_launch(inst, n_ops, ops, left, rght, pmat);
   if (rc) return rc;
   return finish_reduction(inst, lnl, nullptr, warn);
 }

@@ -2113,20 +2113,22 @@ __device__ __forceinline__ void block_reduce_finish(double (&v)[NV], int warn, c
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  // last block: every thread adds a strided subset in index order, thread 0 adds the per-thread sums
+  // last block: the first (up to) 128 threads add a strided subset in index order, thread 0 adds the per-thread sums
   __shared__ double sfin[NV][128];
-  for (int k = 0; k < NV; ++k)
-  {
-    double a = 0.0;
-    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) a += ro.partials[(size_t)b * NV + k];
-    sfin[k][threadIdx.x] = a;
-  }
+  const int         nfin = min((int)blockDim.x, 128);
+  if ((int)threadIdx.x < nfin)
+    for (int k = 0; k < NV; ++k)
+    {
+      double a = 0.0;
+      for (int b = threadIdx.x; b < (int)gridDim.x; b += nfin) a += ro.partials[(size_t)b * NV + k];
+      sfin[k][threadIdx.x] = a;
+    }
   __syncthreads();
   if (threadIdx.x == 0)
   {
     double r[2] = {0.0, 0.0};
     for (int k = 0; k < NV; ++k)
-      for (int t = 0; t < (int)blockDim.x; ++t) r[k] += sfin[k][t];
+      for (int t = 0; t < nfin; ++t) r[k] += sfin[k][t];
     int w = *ro.warn_flag;
     *ro.warn_flag = 0;
     *ro.ticket = 0u;
@@ -2341,32 +2343,55 @@ __global__ void __launch_bounds__(128)
 // K2, 4 states: thread per (site, category) on the blocked layout (the warp reads 1 KB contiguous);
 // lane map as in k_traverse_dna (8 lanes per category), category terms gathered to the category-0
 // lane with shuffles and added in category order, i.e. the same arithmetic as k_edge_lnl.
-template <int NCATG>
-__global__ void __launch_bounds__(128)
-    k_edge_lnl_dna(SideDev left, SideDev rght, const double *__restrict__ P, const ModelDev *__restrict__ mod, int npat,
-                   const double *__restrict__ wght, const short *__restrict__ invar,
-                   const uint32_t *__restrict__ tipmask, double *__restrict__ site_lnl,
-                   double *__restrict__ site_lk_out, double *__restrict__ site_lk_cat, int *__restrict__ fact_sum_scale,
-                   ReduceOut ro)
+// Everything the edge reduction reads and writes (also the argument block of the traversal kernel's fused
+// epilogue: Post_Order_Lk + the site loop of Lk in ONE launch, lk.c:562-645).
+struct EdgeDev
 {
-  constexpr int SW = 32 / NCATG;
-  const int     lane = threadIdx.x & 31, cat = lane / SW;
-  const int     warps_per_block = blockDim.x >> 5, warp = threadIdx.x >> 5;
-  double        p[16], pi[4];
+  SideDev         left, rght;
+  const double   *P;  // P-matrix record of the edge
+  const ModelDev *mod;
+  const double   *wght;
+  const short    *invar;
+  const uint32_t *tipmask;
+  double         *site_lnl, *site_lk_out, *site_lk_cat;
+  int            *fact_sum_scale;
+  int             npat;
+  int             enabled;
+  ReduceOut       ro;
+};
+
+// per-thread constants of the edge reduction: this lane's category of P, pi, the category weight
+template <int NCATG>
+struct EdgeLaneConst
+{
+  double p[16], pi[4], wc;
+  __device__ __forceinline__ void load(const EdgeDev &e, int lane)
+  {
+    const int cat = lane / (32 / NCATG);
 #pragma unroll
-  for (int q = 0; q < 16; ++q) p[q] = P[cat * 16 + q];
+    for (int q = 0; q < 16; ++q) p[q] = e.P[cat * 16 + q];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) pi[q] = mod->pi[q];
-  const double wc = mod->probs[cat];
-  double       acc[1] = {0.0};
-  int          warn = 0;
-  const int    groups = (npat + SW - 1) / SW;
-  for (int grp = blockIdx.x * warps_per_block + warp; grp < groups; grp += gridDim.x * warps_per_block)
+    for (int q = 0; q < 4; ++q) pi[q] = e.mod->pi[q];
+    wc = e.mod->probs[cat];
+  }
+};
+
+// one group of 32 / NCATG sites x NCATG categories (one warp)
+template <int NCATG>
+__device__ __forceinline__ void edge_lnl_dna_group(const EdgeDev &e, const EdgeLaneConst<NCATG> &k, int grp, int lane,
+                                                   double &acc, int &warn)
+{
+  constexpr int   SW = 32 / NCATG;
+  const int       cat = lane / SW;
+  const SideDev  &left = e.left, &rght = e.rght;
+  const int       npat = e.npat;
+  const double (&p)[16] = k.p;
+  const double (&pi)[4] = k.pi;
   {
     const int    site0 = grp * SW + (lane % SW);
     const bool   valid = site0 < npat;
     const int    site = valid ? site0 : npat - 1;
-    const double w = wght[site];
+    const double w = e.wght[site];
     const bool   live = valid && (w > DBL_MIN);  // lk.c:632
     const size_t off = ((((size_t)(site >> 3) * NCATG + cat) << 3) + (site & 7)) * 4;
     double       L[4], R[4];
@@ -2377,7 +2402,7 @@ __global__ void __launch_bounds__(128)
     }
     else
     {
-      const uint32_t m = tipmask[left.tip[site]];
+      const uint32_t m = e.tipmask[left.tip[site]];
 #pragma unroll
       for (int q = 0; q < 4; ++q) L[q] = (double)((m >> q) & 1u);
     }
@@ -2389,7 +2414,7 @@ __global__ void __launch_bounds__(128)
     }
     else
     {
-      rm = tipmask[rght.tip[site]];
+      rm = e.tipmask[rght.tip[site]];
 #pragma unroll
       for (int q = 0; q < 4; ++q) R[q] = (double)((rm >> q) & 1u);
     }
@@ -2400,14 +2425,14 @@ __global__ void __launch_bounds__(128)
       const int st = __ffs(rm) - 1;
       double    q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0, ps = 0.0;
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (k == st)
+      for (int kk = 0; kk < 4; ++kk)
+        if (kk == st)
         {
-          q0 = p[k * 4 + 0] * L[0];
-          q1 = p[k * 4 + 1] * L[1];
-          q2 = p[k * 4 + 2] * L[2];
-          q3 = p[k * 4 + 3] * L[3];
-          ps = pi[k];
+          q0 = p[kk * 4 + 0] * L[0];
+          q1 = p[kk * 4 + 1] * L[1];
+          q2 = p[kk * 4 + 2] * L[2];
+          q3 = p[kk * 4 + 3] * L[3];
+          ps = pi[kk];
         }
       lk = ps * hsum4(q0, q1, q2, q3);
     }
@@ -2415,32 +2440,33 @@ __global__ void __launch_bounds__(128)
     {  // avx.c:125-149
       double x[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
+      for (int kk = 0; kk < 4; ++kk)
       {
         double a = 0.0;
 #pragma unroll
-        for (int l = 0; l < 4; ++l) a = fma(p[k * 4 + l], L[l], a);
-        x[k] = a * (R[k] * pi[k]);
+        for (int l = 0; l < 4; ++l) a = fma(p[kk * 4 + l], L[l], a);
+        x[kk] = a * (R[kk] * pi[kk]);
       }
       lk = hsum4(x[0], x[1], x[2], x[3]);
     }
-    if (live) site_lk_cat[(size_t)site * NCATG + cat] = lk;  // lk.c:2801
+    if (live) e.site_lk_cat[(size_t)site * NCATG + cat] = lk;  // lk.c:2801
     // lk.c:816-818: site_lk = sum_c lk_c w_c in category order, on the category-0 lane
-    double term = lk * wc;
+    double term = lk * k.wc;
     double site_lk = 0.0;
 #pragma unroll
     for (int c = 0; c < NCATG; ++c) site_lk = site_lk + __shfl_sync(0xffffffffu, term, c * SW + (lane % SW));
     if (cat == 0 && live)
     {
+      const ModelDev *mod = e.mod;
       int fact = (left.scale ? left.scale[site] : 0) + (rght.scale ? rght.scale[site] : 0);  // lk.c:2781-2791
       if (mod->invar_flag)
       {  // lk.c:820-842
         bool   ovf;
-        double inv = invariant_lk(fact, invar[site], mod->pi, &ovf);
+        double inv = invariant_lk(fact, e.invar[site], mod->pi, &ovf);
         if (ovf)
         {
           fact = 0;
-          inv = invariant_lk(0, invar[site], mod->pi, &ovf);
+          inv = invariant_lk(0, e.invar[site], mod->pi, &ovf);
           site_lk = inv * mod->pinv;
         }
         else
@@ -2452,13 +2478,462 @@ __global__ void __launch_bounds__(128)
         warn = 1;
       }
       const double lsl = log(site_lk) - kLog2 * fact;  // lk.c:854
-      site_lnl[site] = lsl;
-      site_lk_out[site] = exp(lsl);  // lk.c:857
-      fact_sum_scale[site] = fact;
-      acc[0] += w * lsl;  // lk.c:856
+      e.site_lnl[site] = lsl;
+      e.site_lk_out[site] = exp(lsl);  // lk.c:857
+      e.fact_sum_scale[site] = fact;
+      acc += w * lsl;  // lk.c:856
     }
   }
-  block_reduce_finish<1>(acc, warn, ro);
+}
+
+template <int NCATG>
+__global__ void __launch_bounds__(128) k_edge_lnl_dna(const __grid_constant__ EdgeDev e)
+{
+  constexpr int        SW = 32 / NCATG;
+  const int            lane = threadIdx.x & 31;
+  const int            warps_per_block = blockDim.x >> 5, warp = threadIdx.x >> 5;
+  EdgeLaneConst<NCATG> k;
+  k.load(e, lane);
+  double    acc[1] = {0.0};
+  int       warn = 0;
+  const int groups = (e.npat + SW - 1) / SW;
+  for (int grp = blockIdx.x * warps_per_block + warp; grp < groups; grp += gridDim.x * warps_per_block)
+    edge_lnl_dna_group<NCATG>(e, k, grp, lane, acc[0], warn);
+  block_reduce_finish<1>(acc, warn, e.ro);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 fused traversal, 4 states, fourth generation (default).  ncu of k_traverse_dna3
+// (profiles/ncu_r2_dna3.md): 132 warp instructions per (8 sites x 4 categories x update) of which ~35 are
+// loads / DMMA / DMUL / stores; half of the lanes idle in the epilogue (a C fragment has 8 columns, 4 states
+// fill 4); and a block's chunks are dealt to its warps once for the whole launch, so with 4.4 chunks per warp
+// every update waits for the warps that hold 5.  Three changes:
+//  * a chunk is TWO 8-site blocks X and Y.  Per category and child the update is two chained DMMAs:
+//    C = x_X . B_lo, then C += x_Y . B_hi, where B_lo holds P^T in columns 0..3 (zeros in 4..7) and B_hi holds
+//    it in columns 4..7.  Columns 0..3 of C are then exactly P.x of the X sites (the second DMMA adds
+//    +0.0 to them) and columns 4..7 exactly P.x of the Y sites (ascending-k FMA chain from +0.0, i.e. the
+//    rounding of the reference's AVX_Matrix_Vect_Prod, tools/probes/dmma_order.cu): lanes t < 2 hold
+//    states 2t, 2t+1 of X site g, lanes t >= 2 states 2(t-2), 2(t-2)+1 of Y site g.  All 32 lanes
+//    multiply, take the per-site maximum, rescale and store 16 bytes: half the epilogue instructions
+//    per site, and a store instruction writes two contiguous 256-byte blocks.
+//  * work items (update k, chunk i) are dealt round-robin over the compute warps ACROSS updates
+//    (item n = k * C + i goes to warp n mod W): every warp gets the same number of items whatever C is.
+//    An item needs the previous update of the same chunk, done by another warp: a per-chunk progress counter
+//    in shared memory (release / acquire at CTA scope) orders them.  The previous result is forwarded
+//    through the chunk's shared-memory block as before, now between warps.
+//  * no operand double buffering (the dependent wait is hidden by the other warps): fewer registers, and
+//    the specialised item bodies are straight-line code.
+// Shared memory per block: kT4Stages ring stages + per chunk NCATG x 640 + 64 bytes of forwarding block,
+// a 4-byte progress counter and 16 live flags.
+constexpr int kT4Stages = 4;
+constexpr int kT4MaxTileChunks = 64;  // 1024 sites: 1 KB of tip rows per operand and stage
+template <int NCATG>
+struct __align__(128) T4Stage
+{
+  OpDev   op;  // 96 bytes
+  char    pad[128 - sizeof(OpDev)];
+  double  M[2][NCATG * 64];                // per child: P[cat][i][j] (NCATG*16) or TP[cat][mask][i] (NCATG*64)
+  uint8_t rows[2][kT4MaxTileChunks * 16];  // per tip child: tip-table row of every site of the tile
+};
+template <int NCATG>
+__host__ __device__ constexpr int t4_chunk_bytes()
+{
+  return NCATG * 640 + 64;  // per category: X block at +0, Y block at +320 (conflict-free STS.128); 16 scalers
+}
+template <int NCATG>
+__host__ __device__ inline size_t t4_smem_bytes(int tile_chunks)
+{
+  return (size_t)kT4Stages * sizeof(T4Stage<NCATG>) + (size_t)tile_chunks * (t4_chunk_bytes<NCATG>() + 4 + 16);
+}
+__device__ __forceinline__ int lds32_volatile(uint32_t a)
+{
+  int v;
+  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+
+__device__ __forceinline__ const double *lds_ptr(uint32_t a)
+{
+  unsigned long long v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
+  return reinterpret_cast<const double *>(v);
+}
+// byte offsets inside a T4Stage (shared-memory addresses are kept as 32-bit integers: no generic -> shared
+// conversion and no 64-bit arithmetic in the item loop)
+constexpr uint32_t kT4OffDst = 0, kT4OffDstScale = 8, kT4OffC1 = 16, kT4OffS1 = 24, kT4OffC2 = 40, kT4OffS2 = 48,
+                   kT4OffFlags = 80, kT4OffZero = 96, kT4OffM = 128;
+static_assert(offsetof(OpDev, c1) == kT4OffC1 && offsetof(OpDev, s1) == kT4OffS1 && offsetof(OpDev, c2) == kT4OffC2 &&
+                  offsetof(OpDev, s2) == kT4OffS2 && offsetof(OpDev, flags) == kT4OffFlags &&
+                  offsetof(OpDev, dst_scale) == kT4OffDstScale,
+              "T4 stage offsets");
+
+// one item: the update staged at shared address `sa` applied to the 16 sites of chunk `chunkg` (global chunk
+// index); `fw` = the chunk's forwarding block, `rw` = staged tip rows biased by the tile's first site
+template <int NCATG, int KA, int KB>
+__device__ __forceinline__ void t4_item(uint32_t sa, const double (&bAlo)[NCATG], const double (&bAhi)[NCATG],
+                                        const double (&bBlo)[NCATG], const double (&bBhi)[NCATG], uint32_t fw,
+                                        int chunkg, uint32_t rw, bool live, int lane, int apply_scaling)
+{
+  constexpr uint32_t kRowsB = kT4MaxTileChunks * 16;
+  const int          g = lane >> 2, t = lane & 3, hi = t >> 1, os = hi * 8 + g;
+  const int          site = chunkg * 16 + os;                  // this lane's own site (epilogue)
+  const int          goff = chunkg * (2 * NCATG * 32) + lane;  // A fragments: (block X, category 0) + lane, < 2^31 doubles
+  const uint32_t     fws = fw + NCATG * 640 + os * 4;
+  double             xAX[NCATG], xAY[NCATG], xBX[NCATG], xBY[NCATG];
+  int                scA = 0, scB = 0;
+  uint32_t           rowA = 0, rowB = 0;
+  if (KA == kSrcSlot)
+  {
+    const double *c1 = lds_ptr(sa + kT4OffC1) + goff;
+#pragma unroll
+    for (int c = 0; c < NCATG; ++c)
+    {
+      xAX[c] = ldg64q(c1 + c * 32);
+      xAY[c] = ldg64q(c1 + (NCATG + c) * 32);
+    }
+    scA = ldg32q(reinterpret_cast<const int *>(lds_ptr(sa + kT4OffS1)) + site);
+  }
+  if (KB == kSrcSlot)
+  {
+    const double *c2 = lds_ptr(sa + kT4OffC2) + goff;
+#pragma unroll
+    for (int c = 0; c < NCATG; ++c)
+    {
+      xBX[c] = ldg64q(c2 + c * 32);
+      xBY[c] = ldg64q(c2 + (NCATG + c) * 32);
+    }
+    scB = ldg32q(reinterpret_cast<const int *>(lds_ptr(sa + kT4OffS2)) + site);
+  }
+  if (KA == kSrcFwd)
+  {
+#pragma unroll
+    for (int c = 0; c < NCATG; ++c)
+    {
+      xAX[c] = lds64(fw + c * 640 + lane * 8);
+      xAY[c] = lds64(fw + c * 640 + 320 + lane * 8);
+    }
+    scA = lds32(fws);
+  }
+  if (KA == kSrcTip) rowA = lds8(rw + (uint32_t)site);
+  if (KB == kSrcTip) rowB = lds8(rw + kRowsB + (uint32_t)site);
+
+  const uint32_t MAa = sa + kT4OffM + (uint32_t)(2 * (t & 1)) * 8, MBa = MAa + NCATG * 64 * 8;
+  double         o0[NCATG], o1[NCATG];
+#pragma unroll
+  for (int c = 0; c < NCATG; ++c)
+  {
+    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+    if (KA == kSrcTip)
+      lds128(MAa + (uint32_t)(c * 16 * 32) + rowA * 32, a0, a1);
+    else
+    {
+      dmma884(a0, a1, xAX[c], bAlo[c]);
+      dmma884(a0, a1, xAY[c], bAhi[c]);
+    }
+    if (KB == kSrcTip)
+      lds128(MBa + (uint32_t)(c * 16 * 32) + rowB * 32, b0, b1);
+    else
+    {
+      dmma884(b0, b1, xBX[c], bBlo[c]);
+      dmma884(b0, b1, xBY[c], bBhi[c]);
+    }
+    o0[c] = a0 * b0;
+    o1[c] = a1 * b1;
+  }
+  // avx.c:575-587: both children all ones at a (site, category) (only below fully ambiguous tips) -> the
+  // result is exactly 1.0.  Conservative filter on child A; exact test in the (rare) slow path.
+  bool maybe = false;
+  if (KA == kSrcTip)
+    maybe = (rowA == (uint32_t)kTipRowAllOnes);
+  else
+  {
+#pragma unroll
+    for (int c = 0; c < NCATG; ++c)
+      maybe = maybe || (__double2hiint(xAX[c]) == 0x3FF00000) || (__double2hiint(xAY[c]) == 0x3FF00000);
+  }
+  if (__any_sync(0xffffffffu, maybe))
+  {
+#pragma unroll
+    for (int c = 0; c < NCATG; ++c)
+    {
+      bool pa, pb;
+      if (KA == kSrcTip)
+        pa = (rowA == (uint32_t)kTipRowAllOnes);
+      else
+      {
+        const unsigned bx = __ballot_sync(0xffffffffu, xAX[c] == 1.0), by = __ballot_sync(0xffffffffu, xAY[c] == 1.0);
+        pa = ((((hi ? by : bx) >> (g * 4)) & 0xFu) == 0xFu);
+      }
+      if (KB == kSrcTip)
+        pb = (rowB == (uint32_t)kTipRowAllOnes);
+      else
+      {
+        const unsigned bx = __ballot_sync(0xffffffffu, xBX[c] == 1.0), by = __ballot_sync(0xffffffffu, xBY[c] == 1.0);
+        pb = ((((hi ? by : bx) >> (g * 4)) & 0xFu) == 0xFu);
+      }
+      if (pa && pb) o0[c] = o1[c] = 1.0;
+    }
+  }
+  // avx.c:498-510: per-site maximum over all categories and states as an exponent-word compare (all entries
+  // are >= 0; NaN counts as large, like the reference); the two lanes of a site are neighbours
+  int hmax = 0;
+#pragma unroll
+  for (int c = 0; c < NCATG; ++c) hmax = max(hmax, max(__double2hiint(o0[c]), __double2hiint(o1[c])));
+  hmax = max(hmax, __shfl_xor_sync(0xffffffffu, hmax, 1));
+  int        sco = scA + scB;
+  const bool resc = ((unsigned)hmax < 0x2FF00000u) && apply_scaling;
+  if (__any_sync(0xffffffffu, resc))
+  {
+    if (resc)
+    {
+      const double big = two_to_large();
+#pragma unroll
+      for (int c = 0; c < NCATG; ++c)
+      {
+        o0[c] *= big;
+        o1[c] *= big;
+      }
+      sco += kLarge;
+    }
+  }
+  if (live)
+  {
+    double *dst = const_cast<double *>(lds_ptr(sa + kT4OffDst)) + ((chunkg * 2 + hi) * NCATG * 32 + g * 4 + 2 * (t & 1));
+#pragma unroll
+    for (int c = 0; c < NCATG; ++c) stg128q(dst + c * 32, o0[c], o1[c]);
+    if ((t & 1) == 0) stg32q(reinterpret_cast<int *>(const_cast<double *>(lds_ptr(sa + kT4OffDstScale))) + site, sco);
+  }
+  const uint32_t fwo = fw + hi * 320 + g * 32 + (t & 1) * 16;
+#pragma unroll
+  for (int c = 0; c < NCATG; ++c) sts128(fwo + c * 640, o0[c], o1[c]);
+  if ((t & 1) == 0) sts32(fws, sco);
+}
+
+template <int NCATG, int W>
+__global__ void __launch_bounds__((W + 1) * 32, 1)
+    k_traverse_dna4(const OpDev *__restrict__ ops, int n_ops, int total_chunks, int max_tile_chunks, int n_tiles,
+                    const double *__restrict__ wght, int apply_scaling, const __grid_constant__ EdgeDev edge)
+{
+  constexpr int      S = kT4Stages;
+  static_assert((S & (S - 1)) == 0, "ring depth must be a power of two");
+  constexpr uint32_t PB = NCATG * 16 * sizeof(double);
+  constexpr uint32_t TB = NCATG * 64 * sizeof(double);
+  constexpr uint32_t kStageB = (uint32_t)sizeof(T4Stage<NCATG>);
+  extern __shared__ __align__(128) unsigned char t4_smem[];
+  __shared__ __align__(8) uint64_t               full[S], empty[S];
+  T4Stage<NCATG> *st = reinterpret_cast<T4Stage<NCATG> *>(t4_smem);
+  unsigned char  *fwd = t4_smem + (size_t)S * sizeof(T4Stage<NCATG>);
+  int            *done = reinterpret_cast<int *>(fwd + (size_t)max_tile_chunks * t4_chunk_bytes<NCATG>());
+  unsigned char  *livef = reinterpret_cast<unsigned char *>(done + max_tile_chunks);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0)
+    for (int s = 0; s < S; ++s)
+    {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], W);
+    }
+  if (tid < S * 4) reinterpret_cast<double *>(st[tid >> 2].pad)[tid & 3] = 0.0;  // the zero B-fragment words
+  __syncthreads();
+  const int rounds = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  // tile -> chunks: tiles differ by at most one chunk
+  const int tbase = total_chunks / n_tiles, trem = total_chunks - tbase * n_tiles;
+
+  if (warp == W)
+  {  // ---------------- producer warp: descriptor, both matrices and the tile's tip rows of every update
+    const unsigned total_it = (unsigned)rounds * (unsigned)n_ops;
+    for (unsigned base = 0; base < total_it; base += 32)
+    {
+      const unsigned     my = base + lane;
+      unsigned long long m1 = 0, m2 = 0, r1 = 0, r2 = 0;
+      int                kd = 0;
+      if (my < total_it)
+      {
+        const OpDev *o = ops + (my % (unsigned)n_ops);
+        m1 = (unsigned long long)o->P1;
+        m2 = (unsigned long long)o->P2;
+        r1 = (unsigned long long)o->t1;
+        r2 = (unsigned long long)o->t2;
+        kd = o->flags;
+      }
+      const int cnt = (int)min(32u, total_it - base);
+      for (int j = 0; j < cnt; ++j)
+      {
+        const unsigned long long a1 = __shfl_sync(0xffffffffu, m1, j), a2 = __shfl_sync(0xffffffffu, m2, j);
+        const unsigned long long q1 = __shfl_sync(0xffffffffu, r1, j), q2 = __shfl_sync(0xffffffffu, r2, j);
+        const int                kind = __shfl_sync(0xffffffffu, kd, j);
+        if (lane == 0)
+        {
+          const unsigned it = base + j;
+          const int      s = (int)(it & (S - 1));
+          const uint32_t ph = (it / S) & 1u;
+          const int      tile = (int)blockIdx.x + (int)(it / (unsigned)n_ops) * (int)gridDim.x;
+          const int      chunk0 = tile * tbase + min(tile, trem);
+          const uint32_t rb = (uint32_t)((tbase + (tile < trem ? 1 : 0)) * 16);  // one 16-byte unit per chunk
+          const bool     tipA = (kind & 3) == kSrcTip, tipB = (kind >> 2) == kSrcTip;
+          mbar_wait_backoff(&empty[s], ph ^ 1u);
+          const uint32_t b1 = tipA ? TB : PB;
+          const uint32_t b2 = tipB ? TB : PB;
+          mbar_expect_tx(&full[s], (uint32_t)sizeof(OpDev) + b1 + b2 + (tipA ? rb : 0u) + (tipB ? rb : 0u));
+          tma_bulk_g2s(&st[s].op, ops + (it % (unsigned)n_ops), (uint32_t)sizeof(OpDev), &full[s]);
+          tma_bulk_g2s(st[s].M[0], (const void *)a1, b1, &full[s]);
+          tma_bulk_g2s(st[s].M[1], (const void *)a2, b2, &full[s]);
+          if (tipA) tma_bulk_g2s(st[s].rows[0], (const void *)(q1 + (unsigned long long)chunk0 * 16ull), rb, &full[s]);
+          if (tipB) tma_bulk_g2s(st[s].rows[1], (const void *)(q2 + (unsigned long long)chunk0 * 16ull), rb, &full[s]);
+        }
+        __syncwarp();
+      }
+    }
+  }
+  else
+  {
+
+  // ---------------- compute warps
+  const int      g = lane >> 2, t = lane & 3, os = (t >> 1) * 8 + g;
+  const uint32_t st_a = smem_u32(st), fwd_a = smem_u32(fwd), done_a = smem_u32(done), live_a = smem_u32(livef) + os;
+  const uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty);
+  // B fragments: lane (g, t) holds P[c][g & 3][t] in B_lo if g < 4 and in B_hi otherwise; the other one is read
+  // from a zero word of the stage (no select instructions)
+  const uint32_t bsel = (uint32_t)(((g & 3) * 4 + t) * 8);
+  const uint32_t lo_off = (g < 4) ? (kT4OffM + bsel) : kT4OffZero, hi_off = (g < 4) ? kT4OffZero : (kT4OffM + bsel);
+  const uint32_t lo_step = (g < 4) ? 128u : 0u, hi_step = (g < 4) ? 0u : 128u;  // per category
+  const uint32_t lo_b = (g < 4) ? (uint32_t)(NCATG * 64 * 8) : 0u, hi_b = (g < 4) ? 0u : (uint32_t)(NCATG * 64 * 8);  // child B
+  for (int r = 0; r < rounds; ++r)
+  {
+    const int tile = (int)blockIdx.x + r * (int)gridDim.x;
+    const int chunk0 = tile * tbase + min(tile, trem);
+    const int C = tbase + (tile < trem ? 1 : 0);
+    // per-tile state: progress counters and live flags (avx.c:399: zero-weight patterns are never stored; the
+    // arrays are padded with zero weights)
+    if (r > 0) asm volatile("bar.sync 1, %0;" ::"n"(W * 32) : "memory");
+    for (int q = tid; q < C * 16; q += W * 32) livef[q] = (wght[chunk0 * 16 + q] > DBL_MIN) ? 1 : 0;
+    for (int q = tid; q < C; q += W * 32) done[q] = 0;
+    asm volatile("bar.sync 1, %0;" ::"n"(W * 32) : "memory");
+
+    const unsigned it0 = (unsigned)r * (unsigned)n_ops;
+    int            cur = -1;  // update whose ring stage this warp holds
+    int            k = 0, i = warp;
+    while (i >= C)
+    {
+      i -= C;
+      ++k;
+    }
+    double bAlo[NCATG], bAhi[NCATG], bBlo[NCATG], bBhi[NCATG];
+#pragma unroll
+    for (int c = 0; c < NCATG; ++c) bAlo[c] = bAhi[c] = bBlo[c] = bBhi[c] = 0.0;
+    int      kind = 0;
+    uint32_t sa = st_a;
+    while (true)
+    {
+      const int kk = min(k, n_ops - 1);
+      // walk the ring up to update kk: every warp waits for and releases EVERY update (also those in which it
+      // has no item), so that no warp can run more than the ring depth ahead of another
+      while (cur < kk)
+      {
+        if (cur >= 0)
+        {
+          __syncwarp();
+          if (lane == 0)
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_a + ((it0 + (unsigned)cur) & (S - 1)) * 8)
+                         : "memory");
+        }
+        ++cur;
+        const unsigned it = it0 + (unsigned)cur;
+        const uint32_t fa = full_a + (it & (S - 1)) * 8, par = (it / S) & 1u;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "T4_WAIT:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+            "@p bra T4_DONE;\n\t"
+            "bra T4_WAIT;\n\t"
+            "T4_DONE:\n\t"
+            "}" ::"r"(fa),
+            "r"(par)
+            : "memory");
+      }
+      if (k >= n_ops) break;
+      sa = st_a + ((it0 + (unsigned)k) & (S - 1)) * kStageB;
+      if ((kind >> 8) != k + 1)
+      {  // first item of this warp in update k: operand kinds and B fragments (`kind` = flags | (k + 1) << 8)
+        kind = lds32(sa + kT4OffFlags) | ((k + 1) << 8);
+#pragma unroll
+        for (int c = 0; c < NCATG; ++c)
+        {
+          bAlo[c] = lds64(sa + lo_off + c * lo_step);
+          bAhi[c] = lds64(sa + hi_off + c * hi_step);
+          bBlo[c] = lds64(sa + lo_b + lo_off + c * lo_step);
+          bBhi[c] = lds64(sa + hi_b + hi_off + c * hi_step);
+        }
+      }
+      // the previous update of this chunk (another warp's item) must be complete
+      const uint32_t da = done_a + (uint32_t)i * 4;
+      while (lds32_volatile(da) < k) {}
+      fence_cta();
+      const uint32_t fw = fwd_a + (uint32_t)i * t4_chunk_bytes<NCATG>();
+      const bool     live = lds8(live_a + (uint32_t)(i * 16)) != 0;
+      const uint32_t rw = sa + kT4OffM + 2 * NCATG * 64 * 8 - (uint32_t)(chunk0 * 16);
+      const int      ka = kind & 3, kb = (kind >> 2) & 3;
+#define T4_ITEM(KA, KB) t4_item<NCATG, KA, KB>(sa, bAlo, bAhi, bBlo, bBhi, fw, chunk0 + i, rw, live, lane, apply_scaling)
+      if (ka == kSrcFwd)
+      {
+        if (kb == kSrcTip)
+          T4_ITEM(kSrcFwd, kSrcTip);
+        else
+          T4_ITEM(kSrcFwd, kSrcSlot);
+      }
+      else if (ka == kSrcTip)
+        T4_ITEM(kSrcTip, kSrcTip);
+      else if (kb == kSrcTip)
+        T4_ITEM(kSrcSlot, kSrcTip);
+      else
+        T4_ITEM(kSrcSlot, kSrcSlot);
+#undef T4_ITEM
+      __syncwarp();
+      if (lane == 0)
+      {
+        fence_cta();
+        asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(da), "r"(k + 1) : "memory");
+      }
+      i += W;
+      while (i >= C)
+      {
+        i -= C;
+        ++k;
+      }
+    }
+    // release the last update of the round
+    __syncwarp();
+    if (lane == 0)
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_a + ((it0 + (unsigned)(n_ops - 1)) & (S - 1)) * 8)
+                   : "memory");
+  }
+  }  // compute warps
+
+  // ---------------- fused epilogue: the site loop of Lk() at one edge over this block's tiles + the
+  // deterministic grid reduction (lk.c:605-645).  Every CLV this block reads here was written by its own
+  // warps: the block barrier orders those stores.
+  if (edge.enabled)
+  {
+    if constexpr (NCATG == 4)
+    {
+      __syncthreads();
+      EdgeLaneConst<NCATG> ek;
+      ek.load(edge, lane);
+      double acc[1] = {0.0};
+      int    warn = 0;
+      for (int r = 0; r < rounds; ++r)
+      {
+        const int tile = (int)blockIdx.x + r * (int)gridDim.x;
+        const int chunk0 = tile * tbase + min(tile, trem);
+        const int C = tbase + (tile < trem ? 1 : 0);
+        for (int grp = chunk0 * 2 + warp; grp < (chunk0 + C) * 2; grp += W + 1)  // groups of 8 sites
+          edge_lnl_dna_group<NCATG>(edge, ek, grp, lane, acc[0], warn);
+      }
+      block_reduce_finish<1>(acc, warn, edge.ro);
+    }
+  }
 }
 
 // K4, 4 states: thread per (site, category); dot_prod is [site][catg][4] (plain layout).

@@ -42,7 +42,7 @@ assert OP_DTYPE.itemsize == C.sizeof(_Op)
 EXPORTS = [
     "plk_create", "plk_destroy", "plk_last_error", "plk_sync", "plk_set_pattern_weights",
     "plk_set_tip_table", "plk_set_tip_codes", "plk_set_all_tip_codes", "plk_set_tip_vectors", "plk_set_model", "plk_update_pmats",
-    "plk_set_pmat", "plk_get_pmat", "plk_update_partials", "plk_edge_lnl", "plk_eigen_lr",
+    "plk_set_pmat", "plk_get_pmat", "plk_update_partials", "plk_edge_lnl", "plk_traverse_edge_lnl", "plk_eigen_lr",
     "plk_edge_lnl_dlnl", "plk_edge_lnl_eigen", "plk_get_clv", "plk_set_clv", "plk_get_site_lnl",
     "plk_get_dot_prod", "plk_comm_unique_id", "plk_comm_init", "plk_comm_set_allreduce",
     "plk_comm_p2p_export", "plk_comm_p2p_init", "plk_create_sharded", "plk_n_shards",
@@ -82,6 +82,7 @@ def load_library() -> C.CDLL:
     lib.plk_get_pmat.argtypes = [vp, C.c_int, vp]
     lib.plk_update_partials.argtypes = [vp, C.c_int, vp]
     lib.plk_edge_lnl.argtypes = [vp, _Side, _Side, C.c_int, dp, ip]
+    lib.plk_traverse_edge_lnl.argtypes = [vp, C.c_int, vp, _Side, _Side, C.c_int, dp, ip]
     lib.plk_eigen_lr.argtypes = [vp, _Side, _Side]
     lib.plk_edge_lnl_dlnl.argtypes = [vp, dp, dp, dp, ip]
     lib.plk_edge_lnl_eigen.argtypes = [vp, C.c_double, dp, ip]
@@ -251,6 +252,17 @@ class Engine:
         warn = C.c_int(0)
         self._ck(self.lib.plk_edge_lnl(self.h, _Side(left.tip, left.clv), _Side(rght.tip, rght.clv), pmat,
                                        C.byref(out), C.byref(warn)))
+        self.numerical_warning = warn.value
+        return out.value
+
+    def traverse_edge_lnl(self, ops, left: Side, rght: Side, pmat: int) -> float:
+        """Post_Order_Lk + the edge reduction in one call (one launch for 4-state, 4-category data)."""
+        arr = ops if isinstance(ops, np.ndarray) else pack_ops(ops)
+        out = C.c_double(0.0)
+        warn = C.c_int(0)
+        self._ck(self.lib.plk_traverse_edge_lnl(self.h, len(arr), _ptr(arr) if len(arr) else None,
+                                                _Side(left.tip, left.clv), _Side(rght.tip, rght.clv), pmat,
+                                                C.byref(out), C.byref(warn)))
         self.numerical_warning = warn.value
         return out.value
 

@@ -128,6 +128,14 @@ class LkTree:
             self.Update_All_PMats()               # lk.c:500-505
             self.Update_All_Partial_Lk()          # lk.c:562-564
             b = self.tree.root_edge               # lk.c:578-579
+            if not self.update_eigen_lr and not self.use_eigen_lr and self._queue:
+                # traversal + site loop at the root edge as ONE engine call (plk_traverse_edge_lnl)
+                ops, self._queue = self._queue, []
+                self.n_flush += 1
+                left, rght = self.tree.edge_sides(b)
+                lnl = self.eng.traverse_edge_lnl(ops, left, rght, b)      # lk.c:562-645
+                (self.c_lnL,) = self._reduce([lnl])
+                return self.c_lnL
         elif self.use_eigen_lr == NO:
             self.Update_PMat_At_Given_Edge(b)     # lk.c:515-527
         self._flush()

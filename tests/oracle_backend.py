@@ -133,6 +133,11 @@ class OracleBackend:
                                                _dp(self.clv[op.dst]), _p(self.scale[op.dst]),
                                                self._side(op.c1, keep), _dp(p1), self._side(op.c2, keep), _dp(p2))
 
+    # ---- K1 + K2 (plk_traverse_edge_lnl)
+    def traverse_edge_lnl(self, ops, left, rght, pmat):
+        self.update_partials(ops)
+        return self.edge_lnl(left, rght, pmat)
+
     # ---- K2
     def edge_lnl(self, left, rght, pmat):
         keep = []

@@ -221,3 +221,39 @@ def test_error_paths():
         eng.update_pmats([99], [0.1])                     # handle out of range
     with pytest.raises(EngineError):
         Engine(4, 10, 64, 4, 10, 5)                       # ns unsupported
+
+
+@pytest.mark.parametrize("case", ALL_CASES)
+def test_traverse_edge_lnl_equals_the_two_calls(case):
+    """plk_traverse_edge_lnl (Post_Order_Lk + the site loop of Lk in one call; for 4 states x 4 categories the
+    edge reduction is the epilogue of the traversal kernel) against plk_update_partials + plk_edge_lnl:
+    per-pattern lnL / site_lk / per-category terms / fact_sum_scale bit-identical, the total to the rounding
+    of a different (fixed) partition of the sum, and the reference's golden lnL to 1e-12."""
+    c, a = make(case)
+    _, b = make(case)
+    for eng in (a, b):
+        eng.update_pmats(range(c.tree.n_edges), c.tree.l)
+    c.tree.both_sides = False
+    ops = c.tree.post_order_ops()
+    left, rght = c.tree.edge_sides(c.tree.root_edge)
+    a.update_partials(ops)
+    la = a.edge_lnl(left, rght, c.tree.root_edge)
+    n0 = b.launch_count
+    lb = b.traverse_edge_lnl(ops, left, rght, c.tree.root_edge)
+    n_launch = b.launch_count - n0
+    if c.ns == 4 and c.ncatg == 4:
+        assert n_launch <= 2, n_launch          # the traversal kernel (+ the one-off tip-row translation)
+    assert abs(la - lb) <= 1e-13 * abs(la), (la, lb)
+    assert abs(lb - float(c.g["lnL"])) <= 1e-12 * abs(float(c.g["lnL"]))
+    sa, sb = a.get_site_lnl(), b.get_site_lnl()
+    live = c.g["wght"] > 0
+    for k in ("site_lnl", "site_lk", "fact_sum_scale"):
+        assert np.array_equal(sa[k][live], sb[k][live]), k
+    assert np.array_equal(sa["site_lk_cat"][live], sb["site_lk_cat"][live])
+    # a second evaluation (cached descriptors) and a short list (one update + the edge, as an SPR candidate does)
+    lb2 = b.traverse_edge_lnl(ops, left, rght, c.tree.root_edge)
+    assert lb2 == lb
+    lb3 = b.traverse_edge_lnl(ops[-1:], left, rght, c.tree.root_edge)
+    assert lb3 == lb
+    lb4 = b.traverse_edge_lnl([], left, rght, c.tree.root_edge)
+    assert abs(lb4 - lb) <= 1e-13 * abs(lb)
