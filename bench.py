@@ -132,7 +132,7 @@ def measure(name, rank, world, local, steps, warmup, e2e=True, clocks=True, proc
     import torch
     import torch.distributed as dist
 
-    from phyml_b200.engine import Engine, pack_ops
+    from phyml_b200.engine import Engine, pack_codes4, pack_ops
 
     w = wl.WORKLOADS[name]
     strong = w.n_blocks > 1
@@ -157,13 +157,18 @@ def measure(name, rank, world, local, steps, warmup, e2e=True, clocks=True, proc
     stream = torch.cuda.ExternalStream(eng.stream, device=local)
 
     # host-resident inputs in pinned memory (the e2e leg re-uploads them every step)
-    h_codes = torch.from_numpy(pat.codes).pin_memory()
+    # (4-state data: 4-bit tip codes, two patterns per byte -- plk_set_all_tip_codes_packed4)
+    packed = ns == 4 and os.environ.get("PLK_BENCH_UNPACKED_TIPS") is None
+    h_codes = torch.from_numpy(pack_codes4(pat.codes) if packed else pat.codes).pin_memory()
     h_wght = torch.from_numpy(pat.wght).pin_memory()
     h_invar = torch.from_numpy(pat.invar).pin_memory()
     h_site = torch.empty(P, dtype=torch.float64).pin_memory()
 
     def upload_inputs():
-        eng.set_all_tip_codes(h_codes)
+        if packed:
+            eng.set_all_tip_codes_packed4(h_codes)
+        else:
+            eng.set_all_tip_codes(h_codes)
         eng.set_weights_ptr(h_wght.data_ptr(), h_invar.data_ptr())
         eng.set_model(m)
 

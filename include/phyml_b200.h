@@ -95,6 +95,10 @@ int plk_set_tip_table(plk_instance *inst, int n_codes, const double *vectors);
 int plk_set_tip_codes(plk_instance *inst, int tip, const uint8_t *codes);
 /* all tips at once: row i (n_patterns bytes) of a [n_tips][host_stride] byte matrix is tip i. */
 int plk_set_all_tip_codes(plk_instance *inst, const uint8_t *codes, size_t host_stride);
+/* the same with 4-bit codes, two patterns per byte (low nibble = the even pattern): row i
+ * ((n_patterns + 1) / 2 bytes) of a [n_tips][host_stride] byte matrix is tip i.  For tip tables of at
+ * most 16 codes (nucleotide masks, src/lk.c:26-69): half the host-to-device bytes of a full upload. */
+int plk_set_all_tip_codes_packed4(plk_instance *inst, const uint8_t *packed, size_t host_stride);
 /* reference-format tip: the fp64 0/1 vectors b->p_lk_tip_r [n_patterns][ns] written by
  * Init_Partial_Lk_Tips_Double (src/lk.c:2060-2118); codes and table rows are derived here. */
 int plk_set_tip_vectors(plk_instance *inst, int tip, const double *tip_vectors);

@@ -78,6 +78,7 @@ struct plk_instance
   short    *d_invar = nullptr;
   uint32_t *d_tipmask = nullptr;
   uint8_t  *d_tipcodes = nullptr;
+  uint8_t  *d_tippacked = nullptr;  // staging of plk_set_all_tip_codes_packed4
   uint8_t  *d_tiprows = nullptr;   // ns == 4: codes translated to tip-table rows for the fused kernel
   bool      tiprows_dirty = true;
   size_t    tip_stride = 0;
@@ -135,6 +136,7 @@ struct plk_instance
   int      edge_pmat = 0;
   int    t2_variant = 20;        // PLK_T2_VARIANT: < 10: k_traverse_dna2, 10..19: k_traverse_dna3, >= 20: k_traverse_dna4 (default)
   bool   aa_attr_set = false;
+  int    aa_v2 = 0;              // PLK_AA_V2=1: update-major 20-state kernel, one rate category per warp (k_traverse_aa2; experimental)
   int    blocked = 0;            // CLVs in the blocked layout (ns = 4, 20), see clv_off()
   int    dna_mma = 0;            // use k_traverse_dna_mma (tensor-pipe variant) for ns = 4
   int    mma_u = 2;
@@ -445,6 +447,7 @@ int plk_create(const plk_config *cfg, plk_instance **out)
   if (const char *e = getenv("PLK_TRAV_UMAX")) inst->trav_umax = (atoi(e) == 1) ? 1 : 2;
   if (const char *e = getenv("PLK_DNA_MMA")) inst->dna_mma = atoi(e) != 0;
   if (const char *e = getenv("PLK_TRAV_V1")) inst->trav_v1 = atoi(e) != 0;
+  if (const char *e = getenv("PLK_AA_V2")) inst->aa_v2 = atoi(e) != 0;
   if (const char *e = getenv("PLK_T2_VARIANT")) inst->t2_variant = atoi(e);
   if (const char *e = getenv("PLK_TRAV_BLOCKS_PER_SM")) inst->trav_blocks_per_sm = std::max(1, std::min(4, atoi(e)));
   CREATE_TRY(cudaStreamCreateWithFlags(&inst->stream, cudaStreamNonBlocking));
@@ -523,6 +526,7 @@ void plk_destroy(plk_instance *inst)
   cudaFree(inst->d_invar);
   cudaFree(inst->d_tipmask);
   cudaFree(inst->d_tipcodes);
+  cudaFree(inst->d_tippacked);
   cudaFree(inst->d_tiprows);
   cudaFree(inst->d_model);
   cudaFree(inst->d_pmat);
@@ -645,6 +649,40 @@ int plk_set_all_tip_codes(plk_instance *inst, const uint8_t *codes, size_t host_
     CU_TRY(inst, cudaMemcpy2DAsync(inst->d_tipcodes, inst->tip_stride, codes, host_stride, inst->cfg.n_patterns,
                                    inst->cfg.n_tips, cudaMemcpyHostToDevice, inst->stream));
   inst->tiprows_dirty = true;
+  return PLK_OK;
+}
+
+// 4-bit tip codes: two patterns per byte (low nibble = the even pattern).  Halves the bytes a full upload moves
+// over PCIe (1 byte per (tip, pattern) otherwise holds a 4-bit nucleotide mask); the unpack kernel also writes
+// the tip-table rows the fused traversal kernels read, so no separate translation launch follows.
+int plk_set_all_tip_codes_packed4(plk_instance *inst, const uint8_t *packed, size_t host_stride)
+{
+  ARG_CHECK(inst, packed && host_stride >= ((size_t)inst->cfg.n_patterns + 1) / 2, "plk_set_all_tip_codes_packed4: bad arguments");
+  if (!inst->shards.empty())
+  {
+    for (size_t i = 0; i + 1 < inst->shard_lo.size(); ++i)
+      ARG_CHECK(inst, (inst->shard_lo[i] & 1) == 0, "plk_set_all_tip_codes_packed4: a shard starts on an odd pattern");
+    FOR_SHARDS(inst, plk_set_all_tip_codes_packed4(sh, packed + lo / 2, host_stride));
+    return PLK_OK;
+  }
+  USE_DEVICE(inst);
+  ARG_CHECK(inst, inst->masks.size() <= 16, "plk_set_all_tip_codes_packed4: the tip table has more than 16 codes");
+  const size_t pstride = inst->tip_stride / 2, row = ((size_t)inst->cfg.n_patterns + 1) / 2;
+  if (!inst->d_tippacked)
+  {
+    int rc = dev_alloc(inst, &inst->d_tippacked, pstride * inst->cfg.n_tips);
+    if (rc) return rc;
+    CU_TRY(inst, cudaMemsetAsync(inst->d_tippacked, 0, pstride * inst->cfg.n_tips, inst->stream));
+  }
+  CU_TRY(inst, cudaMemcpy2DAsync(inst->d_tippacked, pstride, packed, host_stride, row, inst->cfg.n_tips,
+                                 cudaMemcpyHostToDevice, inst->stream));
+  const size_t n = pstride * inst->cfg.n_tips;
+  const int    mode = inst->fused_dna ? 1 : (inst->fused_aa ? 2 : 0);
+  k_unpack_codes4<<<(unsigned)std::min<size_t>((n / 8 + 255) / 256 + 1, 8192), 256, 0, inst->stream>>>(
+      inst->d_tippacked, inst->d_tipcodes, mode ? inst->d_tiprows : nullptr, n, inst->d_tipmask, mode);
+  inst->launches++;
+  CU_TRY(inst, cudaGetLastError());
+  inst->tiprows_dirty = false;
   return PLK_OK;
 }
 
@@ -864,8 +902,41 @@ static int launch_traverse_t(plk_instance *inst, const OpDev *d_ops, int n_ops, 
 }
 
 // fused 20-state traversal on the FP64 tensor pipe
+// update-major 20-state traversal, one rate category per warp (k_traverse_aa2)
+template <int NCATG>
+static int launch_traverse_aa2_t(plk_instance *inst, const OpDev *d_ops, int n_ops)
+{
+  const int    total_tiles = (inst->cfg.n_patterns + 7) / 8;  // m-tiles of 8 sites
+  const size_t smem = aa2_smem_bytes<NCATG>();
+  auto         kern = k_traverse_aa2<NCATG>;
+  static size_t smem_set[64] = {};  // per instantiation and device
+  if (smem_set[inst->cfg.device & 63] == 0)
+  {
+    CU_TRY(inst, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set[inst->cfg.device & 63] = smem;
+  }
+  const int       slots = inst->num_sms;
+  const long long per_round = (long long)slots * kAa2MaxTiles;
+  const int       rounds = (int)((total_tiles + per_round - 1) / per_round);
+  const int       n_bt = (int)std::max<long long>(1, std::min<long long>((long long)slots * rounds, total_tiles));
+  const int       grid = std::min(n_bt, slots);
+  kern<<<grid, kAa2Threads, smem, inst->stream>>>(d_ops, n_ops, total_tiles, n_bt, inst->d_wght, inst->d_tipmask,
+                                                  inst->d_tiprows, inst->d_tipcodes, inst->apply_scaling);
+  inst->launches++;
+  CU_TRY(inst, cudaGetLastError());
+  return PLK_OK;
+}
+
 static int launch_traverse_aa(plk_instance *inst, const OpDev *d_ops, int n_ops)
 {
+  if (inst->aa_v2)
+    switch (inst->cfg.ncatg)
+    {
+    case 1: return launch_traverse_aa2_t<1>(inst, d_ops, n_ops);
+    case 2: return launch_traverse_aa2_t<2>(inst, d_ops, n_ops);
+    case 4: return launch_traverse_aa2_t<4>(inst, d_ops, n_ops);
+    case 8: return launch_traverse_aa2_t<8>(inst, d_ops, n_ops);
+    }
   const int    nc = inst->cfg.ncatg, P = inst->cfg.n_patterns;
   const size_t smem = (size_t)kAaStages * aa_stage_bytes(nc);
   if (!inst->aa_attr_set)

@@ -175,6 +175,15 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
                : "memory");
 }
 
+// shared-memory progress counters between warps of a block (release / acquire at CTA scope)
+__device__ __forceinline__ int lds32_volatile(uint32_t a)
+{
+  int v;
+  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------------
 // K0: one block per (P-matrix, rate category); one thread per matrix entry.
 struct PmatJob
@@ -988,6 +997,44 @@ __global__ void k_codes_to_rows20(const uint8_t *__restrict__ codes, uint8_t *__
   {
     const uint32_t m = tipmask[codes[i]] & 0xFFFFFu;
     rows[i] = (__popc(m) == 1) ? (uint8_t)(__ffs(m) - 1) : (m == 0xFFFFFu ? (uint8_t)20 : (uint8_t)255);
+  }
+}
+
+// 4-bit packed tip codes (two patterns per byte, low nibble first) -> 1-byte codes and, for the fused kernels,
+// the tip-table rows (mode 1: 4 states, mode 2: 20 states); 8 packed bytes per thread
+__global__ void k_unpack_codes4(const uint8_t *__restrict__ packed, uint8_t *__restrict__ codes, uint8_t *__restrict__ rows,
+                                size_t n_packed, const uint32_t *__restrict__ tipmask, int mode)
+{
+  __shared__ uint8_t row_of[16];
+  if (threadIdx.x < 16)
+  {
+    const uint32_t m = tipmask[threadIdx.x];
+    uint8_t        r = 0;
+    if (mode == 1)
+      r = (uint8_t)tip_row4((int)m);
+    else if (mode == 2)
+    {
+      const uint32_t mm = m & 0xFFFFFu;
+      r = (__popc(mm) == 1) ? (uint8_t)(__ffs(mm) - 1) : (mm == 0xFFFFFu ? (uint8_t)20 : (uint8_t)255);
+    }
+    row_of[threadIdx.x] = r;
+  }
+  __syncthreads();
+  const size_t n8 = n_packed / 8;  // n_packed is a multiple of 64 (rows are padded to 128 codes)
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x)
+  {
+    const uint2 v = reinterpret_cast<const uint2 *>(packed)[i];
+    uint32_t    c[4], r[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+    {
+      const uint32_t h = (q < 2) ? (v.x >> (16 * q)) & 0xFFFFu : (v.y >> (16 * (q - 2))) & 0xFFFFu;  // 2 packed bytes
+      const uint32_t n0 = h & 15u, n1 = (h >> 4) & 15u, n2 = (h >> 8) & 15u, n3 = (h >> 12) & 15u;
+      c[q] = n0 | (n1 << 8) | (n2 << 16) | (n3 << 24);
+      r[q] = (uint32_t)row_of[n0] | ((uint32_t)row_of[n1] << 8) | ((uint32_t)row_of[n2] << 16) | ((uint32_t)row_of[n3] << 24);
+    }
+    reinterpret_cast<uint4 *>(codes)[i] = make_uint4(c[0], c[1], c[2], c[3]);
+    if (rows) reinterpret_cast<uint4 *>(rows)[i] = make_uint4(r[0], r[1], r[2], r[3]);
   }
 }
 
@@ -1960,6 +2007,321 @@ __global__ void __launch_bounds__(kAaThreads, 1)
 }
 
 // ------------------------------------------------------------------------------------------------
+// K1 fused traversal, 20 states, second generation (opt-in: PLK_AA_V2=1; 1, 2, 4 or 8 rate categories).
+// ncu of k_traverse_aa (profiles/ncu_r1_aa_200x50k.md): DMMA pipe 41 % busy; every (update, category) of
+// every 8-site m-tile re-reads its 2 x 15 B fragments from shared memory (one LDS.64 per DMMA), the A
+// fragments come from L2 without look-ahead, and there are 4 integer instructions per DMMA.  Here:
+//  * a warp is bound to ONE rate category for the whole launch: its B fragments (P of both children,
+//    2 x 15 doubles) are loaded once per update and stay in registers for all the m-tiles of the block
+//    (13-20 of them) -- one LDS.64 per ~15 DMMAs;
+//  * update-major: a block owns its m-tiles for the whole launch, the warps of a category share them
+//    round-robin; the A fragments of the next m-tile are loaded while the current one is multiplied;
+//  * the only coupling between categories is the 2^256 rescaling (per-site maximum over ALL categories,
+//    avx.c:498-510): every warp posts its per-site maximum (exponent word) with a shared-memory atomicMax,
+//    the LAST of the NCATG warps to finish an (update, m-tile) takes the decision, rescales the (rare)
+//    affected sites in place, writes the scalers and publishes the m-tile's progress counter, which the
+//    items of the next update of that m-tile wait for (release / acquire at CTA scope);
+//  * tip rows of the block's sites are staged per update by the producer warp (TMA), general ambiguity
+//    masks are looked up through explicit bases (no pointer arithmetic across allocations).
+// Arithmetic and summation order are those of k_traverse_aa: bit-identical to the reference.
+constexpr int kAa2Stages = 4;
+constexpr int kAa2ComputeWarps = 8;  // + 1 producer warp = 288 threads: 168 registers per thread
+constexpr int kAa2Threads = (kAa2ComputeWarps + 1) * 32;
+constexpr int kAa2MaxTiles = 64;  // m-tiles (8 sites) per block and round: 512 bytes of tip rows per operand
+template <int NCATG>
+struct __align__(128) Aa2Stage
+{
+  OpDev   op;
+  char    pad[128 - sizeof(OpDev)];
+  double  M[2][NCATG * 480];                 // per child: fragment-ordered P (480 per category) or tPx (420)
+  uint8_t rows[2][kAa2MaxTiles * 8 + 16];    // per tip child: tip-table rows of the block's sites (+ alignment slack)
+};
+template <int NCATG>
+__host__ __device__ inline size_t aa2_smem_bytes()
+{
+  return (size_t)kAa2Stages * sizeof(Aa2Stage<NCATG>);
+}
+
+template <int NCATG>
+__global__ void __launch_bounds__(kAa2Threads, 1)
+    k_traverse_aa2(const OpDev *__restrict__ ops, int n_ops, int total_tiles, int n_blocks_tiles,
+                   const double *__restrict__ wght, const uint32_t *__restrict__ tipmask,
+                   const uint8_t *__restrict__ rows_base, const uint8_t *__restrict__ codes_base, int apply_scaling)
+{
+  constexpr int      S = kAa2Stages, W = kAa2ComputeWarps, WPC = W / NCATG;
+  static_assert(W % NCATG == 0, "the compute warps must split evenly over the categories");
+  constexpr uint32_t PB = NCATG * 480 * sizeof(double);  // fragment-ordered P
+  constexpr uint32_t TB = NCATG * 420 * sizeof(double);  // transposed tip table
+  extern __shared__ __align__(128) unsigned char aa2_smem[];
+  __shared__ __align__(8) uint64_t               full[S], empty[S];
+  __shared__ int                                 smax[2][kAa2MaxTiles][8];  // per (update parity, m-tile, site)
+  __shared__ int                                 cnt[kAa2MaxTiles], done[kAa2MaxTiles];
+  __shared__ unsigned char                       livem[kAa2MaxTiles];
+  Aa2Stage<NCATG> *st = reinterpret_cast<Aa2Stage<NCATG> *>(aa2_smem);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0)
+    for (int s = 0; s < S; ++s)
+    {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], W);
+    }
+  __syncthreads();
+  const int n_tiles = n_blocks_tiles;  // block-tiles (groups of m-tiles), dealt to blocks round-robin
+  const int rounds = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int tbase = total_tiles / n_tiles, trem = total_tiles - tbase * n_tiles;
+
+  if (warp == W)
+  {  // ---------------- producer warp
+    const unsigned total_it = (unsigned)rounds * (unsigned)n_ops;
+    for (unsigned base = 0; base < total_it; base += 32)
+    {
+      const unsigned     my = base + lane;
+      unsigned long long m1 = 0, m2 = 0, r1 = 0, r2 = 0;
+      int                kd = 0;
+      if (my < total_it)
+      {
+        const OpDev *o = ops + (my % (unsigned)n_ops);
+        m1 = (unsigned long long)o->P1;
+        m2 = (unsigned long long)o->P2;
+        r1 = (unsigned long long)o->t1;
+        r2 = (unsigned long long)o->t2;
+        kd = o->flags;
+      }
+      const int cnt_it = (int)min(32u, total_it - base);
+      for (int j = 0; j < cnt_it; ++j)
+      {
+        const unsigned long long a1 = __shfl_sync(0xffffffffu, m1, j), a2 = __shfl_sync(0xffffffffu, m2, j);
+        const unsigned long long q1 = __shfl_sync(0xffffffffu, r1, j), q2 = __shfl_sync(0xffffffffu, r2, j);
+        const int                kind = __shfl_sync(0xffffffffu, kd, j);
+        if (lane == 0)
+        {
+          const unsigned it = base + j;
+          const int      s = (int)(it % S);
+          const uint32_t ph = (it / S) & 1u;
+          const int      bt = (int)blockIdx.x + (int)(it / (unsigned)n_ops) * (int)gridDim.x;
+          const int      mt0 = bt * tbase + min(bt, trem), MT = tbase + (bt < trem ? 1 : 0);
+          // tip rows of sites [mt0*8, (mt0+MT)*8): whole 16-byte units from the aligned-down start
+          const unsigned long long off0 = ((unsigned long long)mt0 * 8ull) & ~15ull;
+          const uint32_t           rb = (uint32_t)(((unsigned long long)(mt0 + MT) * 8ull - off0 + 15ull) & ~15ull);
+          const bool               tipA = (kind & 1) != 0, tipB = (kind & 2) != 0;
+          mbar_wait_backoff(&empty[s], ph ^ 1u);
+          const uint32_t b1 = tipA ? TB : PB;
+          const uint32_t b2 = tipB ? TB : PB;
+          mbar_expect_tx(&full[s], (uint32_t)sizeof(OpDev) + b1 + b2 + (tipA ? rb : 0u) + (tipB ? rb : 0u));
+          tma_bulk_g2s(&st[s].op, ops + (it % (unsigned)n_ops), (uint32_t)sizeof(OpDev), &full[s]);
+          tma_bulk_g2s(st[s].M[0], (const void *)a1, b1, &full[s]);
+          tma_bulk_g2s(st[s].M[1], (const void *)a2, b2, &full[s]);
+          if (tipA) tma_bulk_g2s(st[s].rows[0], (const void *)(q1 + off0), rb, &full[s]);
+          if (tipB) tma_bulk_g2s(st[s].rows[1], (const void *)(q2 + off0), rb, &full[s]);
+        }
+        __syncwarp();
+      }
+    }
+    return;
+  }
+
+  // ---------------- compute warps: warp -> (category c, sub-stream); lane -> (site g of the m-tile, t)
+  const int g = lane >> 2, t = lane & 3;
+  const int c = warp / WPC, sub = warp % WPC;
+  unsigned  it = 0;
+  for (int r = 0; r < rounds; ++r)
+  {
+    const int bt = (int)blockIdx.x + r * (int)gridDim.x;
+    const int mt0 = bt * tbase + min(bt, trem), MT = tbase + (bt < trem ? 1 : 0);
+    const int row_bias = (int)(((unsigned)mt0 * 8u) & ~15u);  // first site of the staged tip rows
+    if (r > 0) asm volatile("bar.sync 1, %0;" ::"n"(W * 32) : "memory");
+    for (int q = tid; q < MT; q += W * 32)
+    {
+      unsigned m = 0;
+      for (int b = 0; b < 8; ++b) m |= (wght[(mt0 + q) * 8 + b] > DBL_MIN) ? (1u << b) : 0u;  // padded with zero weights
+      livem[q] = (unsigned char)m;
+      cnt[q] = 0;
+      done[q] = 0;
+    }
+    for (int q = tid; q < 2 * kAa2MaxTiles * 8; q += W * 32) (&smax[0][0][0])[q] = 0;
+    asm volatile("bar.sync 1, %0;" ::"n"(W * 32) : "memory");
+
+    for (int k = 0; k < n_ops; ++k, ++it)
+    {
+      const int              s = (int)(it % S);
+      const Aa2Stage<NCATG> &stg = st[s];
+      mbar_wait(&full[s], (it / S) & 1u);
+      const int     kind = stg.op.flags;
+      const bool    tip1 = (kind & 1) != 0, tip2 = (kind & 2) != 0;
+      const double *c1 = stg.op.c1, *c2 = stg.op.c2;
+      double *const dst = stg.op.dst;
+      // B fragments of this warp's category, resident for all m-tiles of the update
+      double bf1[15], bf2[15];
+      {
+        const double *P1 = stg.M[0] + c * 480 + lane, *P2 = stg.M[1] + c * 480 + lane;
+#pragma unroll
+        for (int j = 0; j < 15; ++j)
+        {
+          bf1[j] = tip1 ? 0.0 : P1[j * 32];
+          bf2[j] = tip2 ? 0.0 : P2[j * 32];
+        }
+      }
+      const double *T1 = stg.M[0] + c * 420, *T2 = stg.M[1] + c * 420;  // tPx of this category (tip children)
+      const int     par = k & 1;
+
+      // software pipeline over this warp's m-tiles: A fragments of the next one are in flight
+      double a1n[5], a2n[5];
+#pragma unroll
+      for (int kk = 0; kk < 5; ++kk) a1n[kk] = a2n[kk] = 0.0;
+      int j = sub;
+      if (j < MT)
+      {
+        while (lds32_volatile(smem_u32(&done[j])) < k) {}
+        fence_cta();
+        const size_t ao = ((size_t)(mt0 + j) * NCATG + c) * 160 + lane;
+        if (!tip1)
+#pragma unroll
+          for (int kk = 0; kk < 5; ++kk) a1n[kk] = ldg64q(c1 + ao + kk * 32);
+        if (!tip2)
+#pragma unroll
+          for (int kk = 0; kk < 5; ++kk) a2n[kk] = ldg64q(c2 + ao + kk * 32);
+      }
+      for (; j < MT; j += WPC)
+      {
+        double a1[5], a2[5];
+#pragma unroll
+        for (int kk = 0; kk < 5; ++kk)
+        {
+          a1[kk] = a1n[kk];
+          a2[kk] = a2n[kk];
+        }
+        const int jn = j + WPC;
+        if (jn < MT)
+        {
+          while (lds32_volatile(smem_u32(&done[jn])) < k) {}
+          fence_cta();
+          const size_t ao = ((size_t)(mt0 + jn) * NCATG + c) * 160 + lane;
+          if (!tip1)
+#pragma unroll
+            for (int kk = 0; kk < 5; ++kk) a1n[kk] = ldg64q(c1 + ao + kk * 32);
+          if (!tip2)
+#pragma unroll
+            for (int kk = 0; kk < 5; ++kk) a2n[kk] = ldg64q(c2 + ao + kk * 32);
+        }
+        const int  site = (mt0 + j) * 8 + g;
+        const bool live = (livem[j] >> g) & 1;
+        double     cf1[6], cf2[6];
+        bool       one1, one2;
+        if (!tip1)
+        {
+          const bool     mine = (a1[0] == 1.0) && (a1[1] == 1.0) && (a1[2] == 1.0) && (a1[3] == 1.0) && (a1[4] == 1.0);
+          const unsigned bal = __ballot_sync(0xffffffffu, mine);
+          one1 = ((bal >> (lane & ~3)) & 0xFu) == 0xFu;
+#pragma unroll
+          for (int q = 0; q < 6; ++q) cf1[q] = 0.0;
+#pragma unroll
+          for (int kk = 0; kk < 5; ++kk)
+#pragma unroll
+            for (int n = 0; n < 3; ++n) dmma884(cf1[2 * n], cf1[2 * n + 1], a1[kk], bf1[n * 5 + kk]);
+        }
+        else
+        {
+          const int row = stg.rows[0][site - row_bias];
+          uint32_t  msk = 0u;
+          if (row > 20) msk = tipmask[codes_base[(stg.op.t1 - rows_base) + site]] & 0xFFFFFu;
+          aa_tip_frag(T1, row, msk, t, cf1);
+          one1 = (row == 20);
+        }
+        if (!tip2)
+        {
+          const bool     mine = (a2[0] == 1.0) && (a2[1] == 1.0) && (a2[2] == 1.0) && (a2[3] == 1.0) && (a2[4] == 1.0);
+          const unsigned bal = __ballot_sync(0xffffffffu, mine);
+          one2 = ((bal >> (lane & ~3)) & 0xFu) == 0xFu;
+#pragma unroll
+          for (int q = 0; q < 6; ++q) cf2[q] = 0.0;
+#pragma unroll
+          for (int kk = 0; kk < 5; ++kk)
+#pragma unroll
+            for (int n = 0; n < 3; ++n) dmma884(cf2[2 * n], cf2[2 * n + 1], a2[kk], bf2[n * 5 + kk]);
+        }
+        else
+        {
+          const int row = stg.rows[1][site - row_bias];
+          uint32_t  msk = 0u;
+          if (row > 20) msk = tipmask[codes_base[(stg.op.t2 - rows_base) + site]] & 0xFFFFFu;
+          aa_tip_frag(T2, row, msk, t, cf2);
+          one2 = (row == 20);
+        }
+        // ---- product, store, per-site maximum of this category (exponent words: all entries >= 0)
+        double    *out = dst + (((size_t)(mt0 + j) * NCATG + c) * 5 + (t >> 1)) * 32 + g * 4 + 2 * (t & 1);
+        const bool ones = one1 && one2;  // avx.c:575-587
+        int        hm = 0;
+#pragma unroll
+        for (int n = 0; n < 3; ++n)
+        {
+          if (n * 8 + 2 * t < 20)
+          {
+            const double o0 = ones ? 1.0 : cf1[2 * n] * cf2[2 * n];
+            const double o1 = ones ? 1.0 : cf1[2 * n + 1] * cf2[2 * n + 1];
+            hm = max(hm, max(__double2hiint(o0), __double2hiint(o1)));
+            if (live) stg128q(out + n * 64, o0, o1);
+          }
+        }
+        hm = max(hm, __shfl_xor_sync(0xffffffffu, hm, 1));
+        hm = max(hm, __shfl_xor_sync(0xffffffffu, hm, 2));
+        if (t == 0) atomicMax(&smax[par][j][g], hm);
+        __syncwarp();
+        int old = 0;
+        if (lane == 0)
+        {
+          fence_cta();  // this warp's stores and maxima before its arrival
+          old = atomicAdd(&cnt[j], 1);
+        }
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if ((old % NCATG) == NCATG - 1)
+        {  // last category of (update k, m-tile j): rescaling decision, scalers, progress counter
+          fence_cta();
+          const int  m = lds32_volatile(smem_u32(&smax[par][j][g]));
+          const bool resc = ((unsigned)m < 0x2FF00000u) && apply_scaling;  // avx.c:498-510
+          int        sco = (tip1 ? 0 : stg.op.s1[site]) + (tip2 ? 0 : stg.op.s2[site]);
+          if (__any_sync(0xffffffffu, resc))
+          {
+            if (resc)
+            {
+              sco += kLarge;
+              if (live)
+              {
+                const double big = two_to_large();
+                for (int cc = 0; cc < NCATG; ++cc)
+                {
+                  double *o2 = dst + (((size_t)(mt0 + j) * NCATG + cc) * 5 + (t >> 1)) * 32 + g * 4 + 2 * (t & 1);
+#pragma unroll
+                  for (int n = 0; n < 3; ++n)
+                    if (n * 8 + 2 * t < 20)
+                    {
+                      double x, y;
+                      ldg128(o2 + n * 64, x, y);
+                      stg128(o2 + n * 64, x * big, y * big);
+                    }
+                }
+              }
+            }
+          }
+          if (live && t == 0) stg.op.dst_scale[site] = sco;
+          __syncwarp();
+          if (t == 0) smax[par][j][g] = 0;  // free the slot for update k + 2
+          __syncwarp();
+          if (lane == 0)
+          {
+            fence_cta();
+            asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(&done[j])), "r"(k + 1) : "memory");
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
 // K1 generic: thread per site, any ns <= 32, any ncatg <= 16.  Same arithmetic order.
 __device__ __forceinline__ double child_dot(const double *__restrict__ Prow, const double *__restrict__ v, uint32_t mask,
                                             bool internal, int ns)
@@ -2545,13 +2907,6 @@ __host__ __device__ inline size_t t4_smem_bytes(int tile_chunks)
 {
   return (size_t)kT4Stages * sizeof(T4Stage<NCATG>) + (size_t)tile_chunks * (t4_chunk_bytes<NCATG>() + 4 + 16);
 }
-__device__ __forceinline__ int lds32_volatile(uint32_t a)
-{
-  int v;
-  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-  return v;
-}
-__device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
 
 __device__ __forceinline__ const double *lds_ptr(uint32_t a)
 {

@@ -41,7 +41,7 @@ assert OP_DTYPE.itemsize == C.sizeof(_Op)
 
 EXPORTS = [
     "plk_create", "plk_destroy", "plk_last_error", "plk_sync", "plk_set_pattern_weights",
-    "plk_set_tip_table", "plk_set_tip_codes", "plk_set_all_tip_codes", "plk_set_tip_vectors", "plk_set_model", "plk_update_pmats",
+    "plk_set_tip_table", "plk_set_tip_codes", "plk_set_all_tip_codes", "plk_set_all_tip_codes_packed4", "plk_set_tip_vectors", "plk_set_model", "plk_update_pmats",
     "plk_set_pmat", "plk_get_pmat", "plk_update_partials", "plk_edge_lnl", "plk_traverse_edge_lnl", "plk_eigen_lr",
     "plk_edge_lnl_dlnl", "plk_edge_lnl_eigen", "plk_get_clv", "plk_set_clv", "plk_get_site_lnl",
     "plk_get_dot_prod", "plk_comm_unique_id", "plk_comm_init", "plk_comm_set_allreduce",
@@ -74,6 +74,7 @@ def load_library() -> C.CDLL:
     lib.plk_set_tip_table.argtypes = [vp, C.c_int, vp]
     lib.plk_set_tip_codes.argtypes = [vp, C.c_int, vp]
     lib.plk_set_all_tip_codes.argtypes = [vp, vp, C.c_size_t]
+    lib.plk_set_all_tip_codes_packed4.argtypes = [vp, vp, C.c_size_t]
     lib.plk_set_tip_vectors.argtypes = [vp, C.c_int, vp]
     lib.plk_set_model.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_double, C.c_int, C.c_double, C.c_double,
                                   C.c_double]
@@ -116,6 +117,15 @@ def pack_ops(ops: Sequence[PartialOp]) -> np.ndarray:
     for i, o in enumerate(ops):
         arr[i] = (o.dst, o.c1.tip, o.c1.clv, o.pmat1, o.c2.tip, o.c2.clv, o.pmat2)
     return arr
+
+
+def pack_codes4(codes: np.ndarray) -> np.ndarray:
+    """[n_tips, P] codes < 16 -> [n_tips, (P + 1) // 2] bytes, low nibble = the even pattern."""
+    c = np.ascontiguousarray(codes, dtype=np.uint8)
+    assert c.ndim == 2 and (c < 16).all()
+    if c.shape[1] & 1:
+        c = np.concatenate([c, np.zeros((c.shape[0], 1), dtype=np.uint8)], axis=1)
+    return np.ascontiguousarray(c[:, 0::2] | (c[:, 1::2] << 4))
 
 
 class Engine:
@@ -203,6 +213,17 @@ class Engine:
             assert c.shape == (self.n_tips, self.P)
             ptr, stride = c.ctypes.data, c.strides[0]
         self._ck(self.lib.plk_set_all_tip_codes(self.h, C.c_void_p(ptr), stride))
+
+    def set_all_tip_codes_packed4(self, packed):
+        """All tips as 4-bit codes, two patterns per byte (``pack_codes4``): [n_tips, (P + 1) // 2] uint8."""
+        if hasattr(packed, "data_ptr"):
+            assert tuple(packed.shape) == (self.n_tips, (self.P + 1) // 2)
+            ptr, stride = packed.data_ptr(), packed.stride(0)
+        else:
+            c = np.ascontiguousarray(packed, dtype=np.uint8)
+            assert c.shape == (self.n_tips, (self.P + 1) // 2)
+            ptr, stride = c.ctypes.data, c.strides[0]
+        self._ck(self.lib.plk_set_all_tip_codes_packed4(self.h, C.c_void_p(ptr), stride))
 
     def set_weights_ptr(self, wght_ptr: int, invar_ptr: int = 0):
         """Weights / invar from raw host pointers (pinned buffers)."""

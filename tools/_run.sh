@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -30 > gpurun_out/r2f_pytest.log
-timeout 600 python bench.py --steps 30 --warmup 5 > gpurun_out/r2f_bench.json 2> gpurun_out/r2f_bench.err
-PLK_NO_FUSED_EDGE=1 timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-secondary > gpurun_out/r2f_nofuse.json 2>&1
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-secondary --workload aa_200x50k > gpurun_out/r2g_aa2.json 2>&1
+PLK_AA_V1=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-secondary --workload aa_200x50k > gpurun_out/r2g_aa1.json 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'k_traverse_aa' -s 2 -c 1 -f -o gpurun_out/prof_aa2 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-secondary --workload aa_200x50k > gpurun_out/ncu_aa2.log 2>&1
