@@ -136,7 +136,7 @@ struct plk_instance
   int      edge_pmat = 0;
   int    t2_variant = 20;        // PLK_T2_VARIANT: < 10: k_traverse_dna2, 10..19: k_traverse_dna3, >= 20: k_traverse_dna4 (default)
   bool   aa_attr_set = false;
-  int    aa_v2 = 0;              // PLK_AA_V2=1: update-major 20-state kernel, one rate category per warp (k_traverse_aa2; experimental)
+  int    aa_v1 = 0;              // PLK_AA_V1=1: first-generation 20-state kernel (k_traverse_aa; also used for ncatg 3, 5, 6, 7)
   int    blocked = 0;            // CLVs in the blocked layout (ns = 4, 20), see clv_off()
   int    dna_mma = 0;            // use k_traverse_dna_mma (tensor-pipe variant) for ns = 4
   int    mma_u = 2;
@@ -447,7 +447,7 @@ int plk_create(const plk_config *cfg, plk_instance **out)
   if (const char *e = getenv("PLK_TRAV_UMAX")) inst->trav_umax = (atoi(e) == 1) ? 1 : 2;
   if (const char *e = getenv("PLK_DNA_MMA")) inst->dna_mma = atoi(e) != 0;
   if (const char *e = getenv("PLK_TRAV_V1")) inst->trav_v1 = atoi(e) != 0;
-  if (const char *e = getenv("PLK_AA_V2")) inst->aa_v2 = atoi(e) != 0;
+  if (const char *e = getenv("PLK_AA_V1")) inst->aa_v1 = atoi(e) != 0;
   if (const char *e = getenv("PLK_T2_VARIANT")) inst->t2_variant = atoi(e);
   if (const char *e = getenv("PLK_TRAV_BLOCKS_PER_SM")) inst->trav_blocks_per_sm = std::max(1, std::min(4, atoi(e)));
   CREATE_TRY(cudaStreamCreateWithFlags(&inst->stream, cudaStreamNonBlocking));
@@ -902,26 +902,30 @@ static int launch_traverse_t(plk_instance *inst, const OpDev *d_ops, int n_ops, 
 }
 
 // fused 20-state traversal on the FP64 tensor pipe
-// update-major 20-state traversal, one rate category per warp (k_traverse_aa2)
+// 20-state traversal, third generation (k_traverse_aa3): the tiling of k_traverse_aa, NCATG at compile time
 template <int NCATG>
-static int launch_traverse_aa2_t(plk_instance *inst, const OpDev *d_ops, int n_ops)
+static int launch_traverse_aa3_t(plk_instance *inst, const OpDev *d_ops, int n_ops)
 {
-  const int    total_tiles = (inst->cfg.n_patterns + 7) / 8;  // m-tiles of 8 sites
-  const size_t smem = aa2_smem_bytes<NCATG>();
-  auto         kern = k_traverse_aa2<NCATG>;
+  const int     P = inst->cfg.n_patterns;
+  const size_t  smem = (size_t)kAa3Stages * sizeof(Aa3Stage<NCATG>);
+  auto          kern = k_traverse_aa3<NCATG>;
   static size_t smem_set[64] = {};  // per instantiation and device
   if (smem_set[inst->cfg.device & 63] == 0)
   {
     CU_TRY(inst, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set[inst->cfg.device & 63] = smem;
   }
-  const int       slots = inst->num_sms;
-  const long long per_round = (long long)slots * kAa2MaxTiles;
-  const int       rounds = (int)((total_tiles + per_round - 1) / per_round);
-  const int       n_bt = (int)std::max<long long>(1, std::min<long long>((long long)slots * rounds, total_tiles));
-  const int       grid = std::min(n_bt, slots);
-  kern<<<grid, kAa2Threads, smem, inst->stream>>>(d_ops, n_ops, total_tiles, n_bt, inst->d_wght, inst->d_tipmask,
-                                                  inst->d_tiprows, inst->d_tipcodes, inst->apply_scaling);
+  const int       slots = inst->num_sms;  // one 512-thread block per SM
+  const long long cap = (long long)slots * kAaTileCap;
+  const int       rounds = (int)((P + cap - 1) / cap);
+  int             n_tiles = std::max(1, std::min(slots * rounds, (P + 7) / 8));
+  int             tile_sites = (P + n_tiles - 1) / n_tiles;
+  tile_sites = ((tile_sites + 7) / 8) * 8;
+  if (tile_sites > kAaTileCap) tile_sites = kAaTileCap;
+  n_tiles = (P + tile_sites - 1) / tile_sites;
+  const int grid = std::min(n_tiles, slots);
+  kern<<<grid, kAaThreads, smem, inst->stream>>>(d_ops, n_ops, P, tile_sites, n_tiles, inst->d_wght, inst->d_tipmask,
+                                                 inst->d_tiprows, inst->d_tipcodes, inst->apply_scaling);
   inst->launches++;
   CU_TRY(inst, cudaGetLastError());
   return PLK_OK;
@@ -929,13 +933,13 @@ static int launch_traverse_aa2_t(plk_instance *inst, const OpDev *d_ops, int n_o
 
 static int launch_traverse_aa(plk_instance *inst, const OpDev *d_ops, int n_ops)
 {
-  if (inst->aa_v2)
+  if (!inst->aa_v1)
     switch (inst->cfg.ncatg)
     {
-    case 1: return launch_traverse_aa2_t<1>(inst, d_ops, n_ops);
-    case 2: return launch_traverse_aa2_t<2>(inst, d_ops, n_ops);
-    case 4: return launch_traverse_aa2_t<4>(inst, d_ops, n_ops);
-    case 8: return launch_traverse_aa2_t<8>(inst, d_ops, n_ops);
+    case 1: return launch_traverse_aa3_t<1>(inst, d_ops, n_ops);
+    case 2: return launch_traverse_aa3_t<2>(inst, d_ops, n_ops);
+    case 4: return launch_traverse_aa3_t<4>(inst, d_ops, n_ops);
+    case 8: return launch_traverse_aa3_t<8>(inst, d_ops, n_ops);
     }
   const int    nc = inst->cfg.ncatg, P = inst->cfg.n_patterns;
   const size_t smem = (size_t)kAaStages * aa_stage_bytes(nc);
@@ -1160,7 +1164,7 @@ static EdgeDev make_edge_dev(plk_instance *inst, plk_side left, plk_side rght, i
 }
 
 // op-major tensor-pipe 4-state traversal, round-robin items (k_traverse_dna4): chunks of two 8-site blocks
-template <int NCATG, int W>
+template <int NCATG, int W, bool PF>
 static int launch_traverse4_t(plk_instance *inst, const OpDev *d_ops, int n_ops)
 {
   constexpr size_t kSmemPerSm = 227 * 1024;
@@ -1175,7 +1179,7 @@ static int launch_traverse4_t(plk_instance *inst, const OpDev *d_ops, int n_ops)
   const int       tile_chunks = (total_chunks + n_tiles - 1) / n_tiles;  // the largest tile
   const int       grid = std::min(n_tiles, slots);
   const size_t    smem = t4_smem_bytes<NCATG>(tile_chunks);
-  auto            kern = k_traverse_dna4<NCATG, W>;
+  auto            kern = k_traverse_dna4<NCATG, W, PF>;
   static size_t   smem_set[64] = {};  // per instantiation and device
   if (smem_set[inst->cfg.device & 63] == 0)
   {
@@ -1207,11 +1211,8 @@ static int launch_traverse4_nc(plk_instance *inst, const OpDev *d_ops, int n_ops
 {
   switch (inst->t2_variant)
   {
-  case 21: return launch_traverse4_t<NCATG, 17>(inst, d_ops, n_ops);
-  case 22: return launch_traverse4_t<NCATG, 19>(inst, d_ops, n_ops);
-  case 23: return launch_traverse4_t<NCATG, 13>(inst, d_ops, n_ops);
-  case 24: return launch_traverse4_t<NCATG, 11>(inst, d_ops, n_ops);
-  default: return launch_traverse4_t<NCATG, 15>(inst, d_ops, n_ops);
+  case 21: return launch_traverse4_t<NCATG, 15, true>(inst, d_ops, n_ops);  // with the L1 look-ahead (measured slower: 0.269 vs 0.249 ms)
+  default: return launch_traverse4_t<NCATG, 15, false>(inst, d_ops, n_ops);
   }
 }
 

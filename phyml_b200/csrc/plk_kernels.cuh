@@ -175,6 +175,8 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
                : "memory");
 }
 
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // shared-memory progress counters between warps of a block (release / acquire at CTA scope)
 __device__ __forceinline__ int lds32_volatile(uint32_t a)
 {
@@ -2006,58 +2008,66 @@ __global__ void __launch_bounds__(kAaThreads, 1)
   }
 }
 
+__device__ __forceinline__ const double *lds_ptr(uint32_t a)
+{
+  unsigned long long v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
+  return reinterpret_cast<const double *>(v);
+}
+// byte offsets inside a T4Stage (shared-memory addresses are kept as 32-bit integers: no generic -> shared
+// conversion and no 64-bit arithmetic in the item loop)
+constexpr uint32_t kT4OffDst = 0, kT4OffDstScale = 8, kT4OffC1 = 16, kT4OffS1 = 24, kT4OffC2 = 40, kT4OffS2 = 48,
+                   kT4OffFlags = 80, kT4OffZero = 96, kT4OffM = 128;
+static_assert(offsetof(OpDev, c1) == kT4OffC1 && offsetof(OpDev, s1) == kT4OffS1 && offsetof(OpDev, c2) == kT4OffC2 &&
+                  offsetof(OpDev, s2) == kT4OffS2 && offsetof(OpDev, flags) == kT4OffFlags &&
+                  offsetof(OpDev, dst_scale) == kT4OffDstScale,
+              "T4 stage offsets");
+
+
 // ------------------------------------------------------------------------------------------------
-// K1 fused traversal, 20 states, second generation (opt-in: PLK_AA_V2=1; 1, 2, 4 or 8 rate categories).
-// ncu of k_traverse_aa (profiles/ncu_r1_aa_200x50k.md): DMMA pipe 41 % busy; every (update, category) of
-// every 8-site m-tile re-reads its 2 x 15 B fragments from shared memory (one LDS.64 per DMMA), the A
-// fragments come from L2 without look-ahead, and there are 4 integer instructions per DMMA.  Here:
-//  * a warp is bound to ONE rate category for the whole launch: its B fragments (P of both children,
-//    2 x 15 doubles) are loaded once per update and stay in registers for all the m-tiles of the block
-//    (13-20 of them) -- one LDS.64 per ~15 DMMAs;
-//  * update-major: a block owns its m-tiles for the whole launch, the warps of a category share them
-//    round-robin; the A fragments of the next m-tile are loaded while the current one is multiplied;
-//  * the only coupling between categories is the 2^256 rescaling (per-site maximum over ALL categories,
-//    avx.c:498-510): every warp posts its per-site maximum (exponent word) with a shared-memory atomicMax,
-//    the LAST of the NCATG warps to finish an (update, m-tile) takes the decision, rescales the (rare)
-//    affected sites in place, writes the scalers and publishes the m-tile's progress counter, which the
-//    items of the next update of that m-tile wait for (release / acquire at CTA scope);
-//  * tip rows of the block's sites are staged per update by the producer warp (TMA), general ambiguity
-//    masks are looked up through explicit bases (no pointer arithmetic across allocations).
-// Arithmetic and summation order are those of k_traverse_aa: bit-identical to the reference.
-constexpr int kAa2Stages = 4;
-constexpr int kAa2ComputeWarps = 8;  // + 1 producer warp = 288 threads: 168 registers per thread
-constexpr int kAa2Threads = (kAa2ComputeWarps + 1) * 32;
-constexpr int kAa2MaxTiles = 64;  // m-tiles (8 sites) per block and round: 512 bytes of tip rows per operand
+// K1 fused traversal, 20 states, third generation (default for 1, 2, 4 or 8 rate categories): the loop nest
+// and the DMMA arithmetic of k_traverse_aa with its overheads removed.  ncu of k_traverse_aa
+// (profiles/ncu_r2_aa_v1.md): on B200 DMMA.8x8x4 executes on the FP64 pipe (4 cycles per SM), and that pipe was
+// also fed 0.8 DSETP/DMNMX per DMMA by the all-ones test (avx.c:575-587) and the running maximum; there
+// were 19 warp instructions per DMMA (integer address arithmetic with a run-time category count, selects,
+// predicate logic) against 16 issue slots per DMMA and scheduler at full pipe rate; tip rows were 1-byte
+// global loads at the head of every update.  Here:
+//  * NCATG is a template parameter, the category loop is unrolled: every fragment address is one base
+//    pointer per (update, m-tile) plus an immediate; the A fragments of category c + 1 are in flight while
+//    category c is multiplied;
+//  * the all-ones rule is a one-compare filter per child and category (exponent word of the first state)
+//    in front of a rarely taken exact path; the per-site maximum is an integer maximum of exponent words:
+//    the FP64 pipe only sees DMMA and the 6 DMUL per category;
+//  * the tile's tip rows are staged per update by the producer warp (TMA); general ambiguity masks are looked
+//    up through explicit bases.
+// The loop nest stays tile-major (a warp walks the whole update list for its 8 sites): measured, the
+// update-major order of k_traverse_dna4 loses here (2.38 vs 2.11 ms) -- a 20-state CLV is 5x larger, one
+// update of all m-tiles no longer fits the L2 window and the children come back from DRAM (1.55 vs 0.48 GB read).
+// Same fragments, same accumulation order: bit-identical to k_traverse_aa and to the reference.
+constexpr int kAa3Stages = 4;
 template <int NCATG>
-struct __align__(128) Aa2Stage
+struct __align__(128) Aa3Stage
 {
   OpDev   op;
   char    pad[128 - sizeof(OpDev)];
-  double  M[2][NCATG * 480];                 // per child: fragment-ordered P (480 per category) or tPx (420)
-  uint8_t rows[2][kAa2MaxTiles * 8 + 16];    // per tip child: tip-table rows of the block's sites (+ alignment slack)
+  double  M[2][NCATG * 480];           // per child: fragment-ordered P (480 per category) or tPx (420)
+  uint8_t rows[2][kAaTileCap + 24];    // per tip child: tip-table rows of the tile's sites (+ alignment slack)
 };
-template <int NCATG>
-__host__ __device__ inline size_t aa2_smem_bytes()
-{
-  return (size_t)kAa2Stages * sizeof(Aa2Stage<NCATG>);
-}
 
 template <int NCATG>
-__global__ void __launch_bounds__(kAa2Threads, 1)
-    k_traverse_aa2(const OpDev *__restrict__ ops, int n_ops, int total_tiles, int n_blocks_tiles,
+__global__ void __launch_bounds__(kAaThreads, 1)
+    k_traverse_aa3(const OpDev *__restrict__ ops, int n_ops, int npat, int tile_sites, int n_tiles,
                    const double *__restrict__ wght, const uint32_t *__restrict__ tipmask,
                    const uint8_t *__restrict__ rows_base, const uint8_t *__restrict__ codes_base, int apply_scaling)
 {
-  constexpr int      S = kAa2Stages, W = kAa2ComputeWarps, WPC = W / NCATG;
-  static_assert(W % NCATG == 0, "the compute warps must split evenly over the categories");
+  constexpr int      S = kAa3Stages, W = kAaComputeWarps;
   constexpr uint32_t PB = NCATG * 480 * sizeof(double);  // fragment-ordered P
   constexpr uint32_t TB = NCATG * 420 * sizeof(double);  // transposed tip table
-  extern __shared__ __align__(128) unsigned char aa2_smem[];
+  constexpr uint32_t kStageB = (uint32_t)sizeof(Aa3Stage<NCATG>);
+  constexpr uint32_t kOffM = 128, kOffRows = 128 + 2 * NCATG * 480 * 8, kRowsB = kAaTileCap + 24;
+  extern __shared__ __align__(128) unsigned char aa3_smem[];
   __shared__ __align__(8) uint64_t               full[S], empty[S];
-  __shared__ int                                 smax[2][kAa2MaxTiles][8];  // per (update parity, m-tile, site)
-  __shared__ int                                 cnt[kAa2MaxTiles], done[kAa2MaxTiles];
-  __shared__ unsigned char                       livem[kAa2MaxTiles];
-  Aa2Stage<NCATG> *st = reinterpret_cast<Aa2Stage<NCATG> *>(aa2_smem);
+  Aa3Stage<NCATG> *st = reinterpret_cast<Aa3Stage<NCATG> *>(aa3_smem);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0)
@@ -2067,13 +2077,11 @@ __global__ void __launch_bounds__(kAa2Threads, 1)
       mbar_init(&empty[s], W);
     }
   __syncthreads();
-  const int n_tiles = n_blocks_tiles;  // block-tiles (groups of m-tiles), dealt to blocks round-robin
-  const int rounds = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  const int tbase = total_tiles / n_tiles, trem = total_tiles - tbase * n_tiles;
+  const int      rounds = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const unsigned total_it = (unsigned)rounds * (unsigned)n_ops;
 
   if (warp == W)
   {  // ---------------- producer warp
-    const unsigned total_it = (unsigned)rounds * (unsigned)n_ops;
     for (unsigned base = 0; base < total_it; base += 32)
     {
       const unsigned     my = base + lane;
@@ -2088,8 +2096,8 @@ __global__ void __launch_bounds__(kAa2Threads, 1)
         r2 = (unsigned long long)o->t2;
         kd = o->flags;
       }
-      const int cnt_it = (int)min(32u, total_it - base);
-      for (int j = 0; j < cnt_it; ++j)
+      const int cnt = (int)min(32u, total_it - base);
+      for (int j = 0; j < cnt; ++j)
       {
         const unsigned long long a1 = __shfl_sync(0xffffffffu, m1, j), a2 = __shfl_sync(0xffffffffu, m2, j);
         const unsigned long long q1 = __shfl_sync(0xffffffffu, r1, j), q2 = __shfl_sync(0xffffffffu, r2, j);
@@ -2099,12 +2107,11 @@ __global__ void __launch_bounds__(kAa2Threads, 1)
           const unsigned it = base + j;
           const int      s = (int)(it % S);
           const uint32_t ph = (it / S) & 1u;
-          const int      bt = (int)blockIdx.x + (int)(it / (unsigned)n_ops) * (int)gridDim.x;
-          const int      mt0 = bt * tbase + min(bt, trem), MT = tbase + (bt < trem ? 1 : 0);
-          // tip rows of sites [mt0*8, (mt0+MT)*8): whole 16-byte units from the aligned-down start
-          const unsigned long long off0 = ((unsigned long long)mt0 * 8ull) & ~15ull;
-          const uint32_t           rb = (uint32_t)(((unsigned long long)(mt0 + MT) * 8ull - off0 + 15ull) & ~15ull);
-          const bool               tipA = (kind & 1) != 0, tipB = (kind & 2) != 0;
+          const int      tile = (int)blockIdx.x + (int)(it / (unsigned)n_ops) * (int)gridDim.x;
+          const unsigned base_site = (unsigned)tile * (unsigned)tile_sites;
+          const unsigned off0 = base_site & ~15u;  // 16-byte units from the aligned-down start (rows are padded)
+          const uint32_t rb = (base_site - off0 + (unsigned)tile_sites + 15u) & ~15u;
+          const bool     tipA = (kind & 1) != 0, tipB = (kind & 2) != 0;
           mbar_wait_backoff(&empty[s], ph ^ 1u);
           const uint32_t b1 = tipA ? TB : PB;
           const uint32_t b2 = tipB ? TB : PB;
@@ -2121,205 +2128,219 @@ __global__ void __launch_bounds__(kAa2Threads, 1)
     return;
   }
 
-  // ---------------- compute warps: warp -> (category c, sub-stream); lane -> (site g of the m-tile, t)
-  const int g = lane >> 2, t = lane & 3;
-  const int c = warp / WPC, sub = warp % WPC;
-  unsigned  it = 0;
+  // ---------------- compute warps: one m-tile (8 sites) per warp and round; lane -> (site g, t)
+  const int      g = lane >> 2, t = lane & 3;
+  const uint32_t st_a = smem_u32(st), full_a = smem_u32(full), empty_a = smem_u32(empty);
+  unsigned       it = 0;
   for (int r = 0; r < rounds; ++r)
   {
-    const int bt = (int)blockIdx.x + r * (int)gridDim.x;
-    const int mt0 = bt * tbase + min(bt, trem), MT = tbase + (bt < trem ? 1 : 0);
-    const int row_bias = (int)(((unsigned)mt0 * 8u) & ~15u);  // first site of the staged tip rows
-    if (r > 0) asm volatile("bar.sync 1, %0;" ::"n"(W * 32) : "memory");
-    for (int q = tid; q < MT; q += W * 32)
-    {
-      unsigned m = 0;
-      for (int b = 0; b < 8; ++b) m |= (wght[(mt0 + q) * 8 + b] > DBL_MIN) ? (1u << b) : 0u;  // padded with zero weights
-      livem[q] = (unsigned char)m;
-      cnt[q] = 0;
-      done[q] = 0;
-    }
-    for (int q = tid; q < 2 * kAa2MaxTiles * 8; q += W * 32) (&smax[0][0][0])[q] = 0;
-    asm volatile("bar.sync 1, %0;" ::"n"(W * 32) : "memory");
+    const int  tile = (int)blockIdx.x + r * (int)gridDim.x;
+    const int  base_site = tile * tile_sites;
+    const int  n_sites = min(tile_sites, npat - base_site);
+    const bool active = warp * 8 < n_sites;              // warps beyond the tile only keep the ring protocol
+    const int  site = base_site + warp * 8 + g;          // arrays are padded: sites past the end are readable
+    const bool live = active && (site < npat) && (wght[site] > DBL_MIN);
+    const int  row_off = site - (int)((unsigned)base_site & ~15u);
+    const size_t mo = (size_t)(site >> 3) * (NCATG * 160);  // doubles: [m-tile][catg][5][8][4]
 
     for (int k = 0; k < n_ops; ++k, ++it)
     {
-      const int              s = (int)(it % S);
-      const Aa2Stage<NCATG> &stg = st[s];
-      mbar_wait(&full[s], (it / S) & 1u);
-      const int     kind = stg.op.flags;
-      const bool    tip1 = (kind & 1) != 0, tip2 = (kind & 2) != 0;
-      const double *c1 = stg.op.c1, *c2 = stg.op.c2;
-      double *const dst = stg.op.dst;
-      // B fragments of this warp's category, resident for all m-tiles of the update
-      double bf1[15], bf2[15];
+      const uint32_t s = it % S, sa = st_a + s * kStageB;
       {
-        const double *P1 = stg.M[0] + c * 480 + lane, *P2 = stg.M[1] + c * 480 + lane;
-#pragma unroll
-        for (int j = 0; j < 15; ++j)
-        {
-          bf1[j] = tip1 ? 0.0 : P1[j * 32];
-          bf2[j] = tip2 ? 0.0 : P2[j * 32];
-        }
+        const uint32_t fa = full_a + s * 8, par = (it / S) & 1u;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "AA3_WAIT:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+            "@p bra AA3_DONE;\n\t"
+            "bra AA3_WAIT;\n\t"
+            "AA3_DONE:\n\t"
+            "}" ::"r"(fa),
+            "r"(par)
+            : "memory");
       }
-      const double *T1 = stg.M[0] + c * 420, *T2 = stg.M[1] + c * 420;  // tPx of this category (tip children)
-      const int     par = k & 1;
+      if (active)
+      {
+        const int     kind = lds32(sa + kT4OffFlags);
+        const bool    tip1 = (kind & 1) != 0, tip2 = (kind & 2) != 0;
+        const double *a1p = lds_ptr(sa + kT4OffC1) + mo + lane, *a2p = lds_ptr(sa + kT4OffC2) + mo + lane;
+        double       *outp = const_cast<double *>(lds_ptr(sa + kT4OffDst)) + mo + (t >> 1) * 32 + g * 4 + 2 * (t & 1);
+        const uint32_t M1a = sa + kOffM, M2a = M1a + NCATG * 480 * 8;
+        int      sc = 0, row1 = 0, row2 = 0;
+        uint32_t msk1 = 0u, msk2 = 0u;
+        if (tip1)
+        {
+          row1 = (int)lds8(sa + kOffRows + (uint32_t)row_off);
+          if (row1 > 20)
+            msk1 = tipmask[codes_base[(reinterpret_cast<const uint8_t *>(lds_ptr(sa + 32)) - rows_base) + site]] & 0xFFFFFu;
+        }
+        else
+          sc += ldg32q(reinterpret_cast<const int *>(lds_ptr(sa + kT4OffS1)) + site);
+        if (tip2)
+        {
+          row2 = (int)lds8(sa + kOffRows + kRowsB + (uint32_t)row_off);
+          if (row2 > 20)
+            msk2 = tipmask[codes_base[(reinterpret_cast<const uint8_t *>(lds_ptr(sa + 56)) - rows_base) + site]] & 0xFFFFFu;
+        }
+        else
+          sc += ldg32q(reinterpret_cast<const int *>(lds_ptr(sa + kT4OffS2)) + site);
 
-      // software pipeline over this warp's m-tiles: A fragments of the next one are in flight
-      double a1n[5], a2n[5];
+        int hm = 0;
+        // software pipeline over the categories: the A fragments of category c + 1 are in flight while c is multiplied
+        double a1n[5], a2n[5];
 #pragma unroll
-      for (int kk = 0; kk < 5; ++kk) a1n[kk] = a2n[kk] = 0.0;
-      int j = sub;
-      if (j < MT)
-      {
-        while (lds32_volatile(smem_u32(&done[j])) < k) {}
-        fence_cta();
-        const size_t ao = ((size_t)(mt0 + j) * NCATG + c) * 160 + lane;
-        if (!tip1)
-#pragma unroll
-          for (int kk = 0; kk < 5; ++kk) a1n[kk] = ldg64q(c1 + ao + kk * 32);
-        if (!tip2)
-#pragma unroll
-          for (int kk = 0; kk < 5; ++kk) a2n[kk] = ldg64q(c2 + ao + kk * 32);
-      }
-      for (; j < MT; j += WPC)
-      {
-        double a1[5], a2[5];
-#pragma unroll
-        for (int kk = 0; kk < 5; ++kk)
-        {
-          a1[kk] = a1n[kk];
-          a2[kk] = a2n[kk];
-        }
-        const int jn = j + WPC;
-        if (jn < MT)
-        {
-          while (lds32_volatile(smem_u32(&done[jn])) < k) {}
-          fence_cta();
-          const size_t ao = ((size_t)(mt0 + jn) * NCATG + c) * 160 + lane;
-          if (!tip1)
-#pragma unroll
-            for (int kk = 0; kk < 5; ++kk) a1n[kk] = ldg64q(c1 + ao + kk * 32);
-          if (!tip2)
-#pragma unroll
-            for (int kk = 0; kk < 5; ++kk) a2n[kk] = ldg64q(c2 + ao + kk * 32);
-        }
-        const int  site = (mt0 + j) * 8 + g;
-        const bool live = (livem[j] >> g) & 1;
-        double     cf1[6], cf2[6];
-        bool       one1, one2;
+        for (int kk = 0; kk < 5; ++kk) a1n[kk] = a2n[kk] = 0.0;
         if (!tip1)
         {
-          const bool     mine = (a1[0] == 1.0) && (a1[1] == 1.0) && (a1[2] == 1.0) && (a1[3] == 1.0) && (a1[4] == 1.0);
-          const unsigned bal = __ballot_sync(0xffffffffu, mine);
-          one1 = ((bal >> (lane & ~3)) & 0xFu) == 0xFu;
 #pragma unroll
-          for (int q = 0; q < 6; ++q) cf1[q] = 0.0;
-#pragma unroll
-          for (int kk = 0; kk < 5; ++kk)
-#pragma unroll
-            for (int n = 0; n < 3; ++n) dmma884(cf1[2 * n], cf1[2 * n + 1], a1[kk], bf1[n * 5 + kk]);
-        }
-        else
-        {
-          const int row = stg.rows[0][site - row_bias];
-          uint32_t  msk = 0u;
-          if (row > 20) msk = tipmask[codes_base[(stg.op.t1 - rows_base) + site]] & 0xFFFFFu;
-          aa_tip_frag(T1, row, msk, t, cf1);
-          one1 = (row == 20);
+          for (int kk = 0; kk < 5; ++kk) a1n[kk] = ldg64q(a1p + kk * 32);
         }
         if (!tip2)
         {
-          const bool     mine = (a2[0] == 1.0) && (a2[1] == 1.0) && (a2[2] == 1.0) && (a2[3] == 1.0) && (a2[4] == 1.0);
-          const unsigned bal = __ballot_sync(0xffffffffu, mine);
-          one2 = ((bal >> (lane & ~3)) & 0xFu) == 0xFu;
 #pragma unroll
-          for (int q = 0; q < 6; ++q) cf2[q] = 0.0;
+          for (int kk = 0; kk < 5; ++kk) a2n[kk] = ldg64q(a2p + kk * 32);
+        }
+#pragma unroll
+        for (int c = 0; c < NCATG; ++c)
+        {
+          double a1[5], a2[5], cf1[6], cf2[6];
+          bool   f1, f2;  // all-ones filters (avx.c:575-587)
 #pragma unroll
           for (int kk = 0; kk < 5; ++kk)
-#pragma unroll
-            for (int n = 0; n < 3; ++n) dmma884(cf2[2 * n], cf2[2 * n + 1], a2[kk], bf2[n * 5 + kk]);
-        }
-        else
-        {
-          const int row = stg.rows[1][site - row_bias];
-          uint32_t  msk = 0u;
-          if (row > 20) msk = tipmask[codes_base[(stg.op.t2 - rows_base) + site]] & 0xFFFFFu;
-          aa_tip_frag(T2, row, msk, t, cf2);
-          one2 = (row == 20);
-        }
-        // ---- product, store, per-site maximum of this category (exponent words: all entries >= 0)
-        double    *out = dst + (((size_t)(mt0 + j) * NCATG + c) * 5 + (t >> 1)) * 32 + g * 4 + 2 * (t & 1);
-        const bool ones = one1 && one2;  // avx.c:575-587
-        int        hm = 0;
-#pragma unroll
-        for (int n = 0; n < 3; ++n)
-        {
-          if (n * 8 + 2 * t < 20)
           {
-            const double o0 = ones ? 1.0 : cf1[2 * n] * cf2[2 * n];
-            const double o1 = ones ? 1.0 : cf1[2 * n + 1] * cf2[2 * n + 1];
-            hm = max(hm, max(__double2hiint(o0), __double2hiint(o1)));
-            if (live) stg128q(out + n * 64, o0, o1);
+            a1[kk] = a1n[kk];
+            a2[kk] = a2n[kk];
           }
-        }
-        hm = max(hm, __shfl_xor_sync(0xffffffffu, hm, 1));
-        hm = max(hm, __shfl_xor_sync(0xffffffffu, hm, 2));
-        if (t == 0) atomicMax(&smax[par][j][g], hm);
-        __syncwarp();
-        int old = 0;
-        if (lane == 0)
-        {
-          fence_cta();  // this warp's stores and maxima before its arrival
-          old = atomicAdd(&cnt[j], 1);
-        }
-        old = __shfl_sync(0xffffffffu, old, 0);
-        if ((old % NCATG) == NCATG - 1)
-        {  // last category of (update k, m-tile j): rescaling decision, scalers, progress counter
-          fence_cta();
-          const int  m = lds32_volatile(smem_u32(&smax[par][j][g]));
-          const bool resc = ((unsigned)m < 0x2FF00000u) && apply_scaling;  // avx.c:498-510
-          int        sco = (tip1 ? 0 : stg.op.s1[site]) + (tip2 ? 0 : stg.op.s2[site]);
-          if (__any_sync(0xffffffffu, resc))
+          if (c + 1 < NCATG)
           {
-            if (resc)
+            if (!tip1)
             {
-              sco += kLarge;
-              if (live)
-              {
-                const double big = two_to_large();
-                for (int cc = 0; cc < NCATG; ++cc)
-                {
-                  double *o2 = dst + (((size_t)(mt0 + j) * NCATG + cc) * 5 + (t >> 1)) * 32 + g * 4 + 2 * (t & 1);
 #pragma unroll
-                  for (int n = 0; n < 3; ++n)
-                    if (n * 8 + 2 * t < 20)
-                    {
-                      double x, y;
-                      ldg128(o2 + n * 64, x, y);
-                      stg128(o2 + n * 64, x * big, y * big);
-                    }
-                }
-              }
+              for (int kk = 0; kk < 5; ++kk) a1n[kk] = ldg64q(a1p + (c + 1) * 160 + kk * 32);
+            }
+            if (!tip2)
+            {
+#pragma unroll
+              for (int kk = 0; kk < 5; ++kk) a2n[kk] = ldg64q(a2p + (c + 1) * 160 + kk * 32);
             }
           }
-          if (live && t == 0) stg.op.dst_scale[site] = sco;
-          __syncwarp();
-          if (t == 0) smax[par][j][g] = 0;  // free the slot for update k + 2
-          __syncwarp();
-          if (lane == 0)
+          if (!tip1)
           {
-            fence_cta();
-            asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(&done[j])), "r"(k + 1) : "memory");
+            const uint32_t Pf = M1a + (uint32_t)(c * 480 + lane) * 8;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) cf1[q] = 0.0;
+            // k outermost: the three n-tile accumulators advance together (independent MMA chains)
+#pragma unroll
+            for (int kk = 0; kk < 5; ++kk)
+#pragma unroll
+              for (int n = 0; n < 3; ++n) dmma884(cf1[2 * n], cf1[2 * n + 1], a1[kk], lds64(Pf + (n * 5 + kk) * 256));
+            f1 = __double2hiint(a1[0]) == 0x3FF00000;
+          }
+          else
+          {
+            if (row1 <= 20)
+            {
+              const uint32_t T = M1a + (uint32_t)(c * 420 + row1 * 20 + 2 * t) * 8;
+              lds128(T, cf1[0], cf1[1]);
+              lds128(T + 64, cf1[2], cf1[3]);
+              cf1[4] = cf1[5] = 0.0;
+              if (t < 2) lds128(T + 128, cf1[4], cf1[5]);
+            }
+            else
+              aa_tip_frag(reinterpret_cast<const double *>(&st[s].M[0][c * 420]), row1, msk1, t, cf1);
+            f1 = (row1 == 20);
+          }
+          if (!tip2)
+          {
+            const uint32_t Pf = M2a + (uint32_t)(c * 480 + lane) * 8;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) cf2[q] = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < 5; ++kk)
+#pragma unroll
+              for (int n = 0; n < 3; ++n) dmma884(cf2[2 * n], cf2[2 * n + 1], a2[kk], lds64(Pf + (n * 5 + kk) * 256));
+            f2 = __double2hiint(a2[0]) == 0x3FF00000;
+          }
+          else
+          {
+            if (row2 <= 20)
+            {
+              const uint32_t T = M2a + (uint32_t)(c * 420 + row2 * 20 + 2 * t) * 8;
+              lds128(T, cf2[0], cf2[1]);
+              lds128(T + 64, cf2[2], cf2[3]);
+              cf2[4] = cf2[5] = 0.0;
+              if (t < 2) lds128(T + 128, cf2[4], cf2[5]);
+            }
+            else
+              aa_tip_frag(reinterpret_cast<const double *>(&st[s].M[1][c * 420]), row2, msk2, t, cf2);
+            f2 = (row2 == 20);
+          }
+          double o[6];
+#pragma unroll
+          for (int q = 0; q < 6; ++q) o[q] = cf1[q] * cf2[q];
+          if (__any_sync(0xffffffffu, f1 && f2))
+          {  // exact test: all 20 states of both children are 1.0 at this (site, category)
+            bool one1 = f1, one2 = f2;
+            if (!tip1)
+            {
+              const bool mine = (a1[0] == 1.0) && (a1[1] == 1.0) && (a1[2] == 1.0) && (a1[3] == 1.0) && (a1[4] == 1.0);
+              one1 = ((__ballot_sync(0xffffffffu, mine) >> (lane & ~3)) & 0xFu) == 0xFu;
+            }
+            if (!tip2)
+            {
+              const bool mine = (a2[0] == 1.0) && (a2[1] == 1.0) && (a2[2] == 1.0) && (a2[3] == 1.0) && (a2[4] == 1.0);
+              one2 = ((__ballot_sync(0xffffffffu, mine) >> (lane & ~3)) & 0xFu) == 0xFu;
+            }
+            if (one1 && one2)
+            {
+#pragma unroll
+              for (int q = 0; q < 6; ++q) o[q] = 1.0;
+            }
+          }
+          // states n*8 + 2t, +1: the third n-tile only holds states 16..19 (t < 2)
+          hm = max(hm, max(max(__double2hiint(o[0]), __double2hiint(o[1])), max(__double2hiint(o[2]), __double2hiint(o[3]))));
+          if (t < 2) hm = max(hm, max(__double2hiint(o[4]), __double2hiint(o[5])));
+          if (live)
+          {
+            stg128q(outp + c * 160, o[0], o[1]);
+            stg128q(outp + c * 160 + 64, o[2], o[3]);
+            if (t < 2) stg128q(outp + c * 160 + 128, o[4], o[5]);
           }
         }
+        // ---- per-site maximum over all categories and states (exponent words: all entries >= 0; NaN counts as
+        // large like the reference), rescaling (avx.c:498-510)
+        hm = max(hm, __shfl_xor_sync(0xffffffffu, hm, 1));
+        hm = max(hm, __shfl_xor_sync(0xffffffffu, hm, 2));
+        const bool resc = ((unsigned)hm < 0x2FF00000u) && apply_scaling;
+        if (__any_sync(0xffffffffu, resc))
+        {
+          if (resc)
+          {
+            sc += kLarge;
+            if (live)
+            {
+              const double big = two_to_large();
+#pragma unroll 1
+              for (int c = 0; c < NCATG; ++c)
+#pragma unroll
+                for (int n = 0; n < 3; ++n)
+                  if (n * 8 + 2 * t < 20)
+                  {
+                    double x, y;
+                    ldg128(outp + c * 160 + n * 64, x, y);
+                    stg128(outp + c * 160 + n * 64, x * big, y * big);
+                  }
+            }
+          }
+        }
+        if (live && t == 0) stg32q(reinterpret_cast<int *>(const_cast<double *>(lds_ptr(sa + kT4OffDstScale))) + site, sc);
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_a + s * 8) : "memory");
     }
   }
 }
-
 
 // ------------------------------------------------------------------------------------------------
 // K1 generic: thread per site, any ns <= 32, any ncatg <= 16.  Same arithmetic order.
@@ -2908,21 +2929,6 @@ __host__ __device__ inline size_t t4_smem_bytes(int tile_chunks)
   return (size_t)kT4Stages * sizeof(T4Stage<NCATG>) + (size_t)tile_chunks * (t4_chunk_bytes<NCATG>() + 4 + 16);
 }
 
-__device__ __forceinline__ const double *lds_ptr(uint32_t a)
-{
-  unsigned long long v;
-  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
-  return reinterpret_cast<const double *>(v);
-}
-// byte offsets inside a T4Stage (shared-memory addresses are kept as 32-bit integers: no generic -> shared
-// conversion and no 64-bit arithmetic in the item loop)
-constexpr uint32_t kT4OffDst = 0, kT4OffDstScale = 8, kT4OffC1 = 16, kT4OffS1 = 24, kT4OffC2 = 40, kT4OffS2 = 48,
-                   kT4OffFlags = 80, kT4OffZero = 96, kT4OffM = 128;
-static_assert(offsetof(OpDev, c1) == kT4OffC1 && offsetof(OpDev, s1) == kT4OffS1 && offsetof(OpDev, c2) == kT4OffC2 &&
-                  offsetof(OpDev, s2) == kT4OffS2 && offsetof(OpDev, flags) == kT4OffFlags &&
-                  offsetof(OpDev, dst_scale) == kT4OffDstScale,
-              "T4 stage offsets");
-
 // one item: the update staged at shared address `sa` applied to the 16 sites of chunk `chunkg` (global chunk
 // index); `fw` = the chunk's forwarding block, `rw` = staged tip rows biased by the tile's first site
 template <int NCATG, int KA, int KB>
@@ -3065,7 +3071,7 @@ __device__ __forceinline__ void t4_item(uint32_t sa, const double (&bAlo)[NCATG]
   if ((t & 1) == 0) sts32(fws, sco);
 }
 
-template <int NCATG, int W>
+template <int NCATG, int W, bool PF>
 __global__ void __launch_bounds__((W + 1) * 32, 1)
     k_traverse_dna4(const OpDev *__restrict__ ops, int n_ops, int total_chunks, int max_tile_chunks, int n_tiles,
                     const double *__restrict__ wght, int apply_scaling, const __grid_constant__ EdgeDev edge)
@@ -3256,6 +3262,34 @@ __global__ void __launch_bounds__((W + 1) * 32, 1)
       {
         i -= C;
         ++k;
+      }
+      if (PF && k < n_ops)
+      {  // pull the global operands of this warp's NEXT item into L1 (one 2 KB chunk per operand: 16 lines).
+         // Its descriptor is read if its ring stage is already full (the producer runs ahead); never waits.
+        const unsigned itn = it0 + (unsigned)k;
+        const uint32_t san = st_a + (itn & (S - 1)) * kStageB;
+        bool           ready = (san == sa) && ((kind >> 8) == k + 1);
+        if (!ready)
+        {
+          uint32_t ok;
+          asm volatile(
+              "{\n\t"
+              ".reg .pred p;\n\t"
+              "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+              "selp.u32 %0, 1, 0, p;\n\t"
+              "}"
+              : "=r"(ok)
+              : "r"(full_a + (itn & (S - 1)) * 8), "r"((itn / S) & 1u)
+              : "memory");
+          ready = ok != 0;
+        }
+        if (ready && lane < 16)
+        {
+          const int    fl = lds32(san + kT4OffFlags);
+          const size_t po = (size_t)(chunk0 + i) * (2 * NCATG * 32) + lane * 16;
+          if ((fl & 3) == kSrcSlot) prefetch_l1(lds_ptr(san + kT4OffC1) + po);
+          if (((fl >> 2) & 3) == kSrcSlot) prefetch_l1(lds_ptr(san + kT4OffC2) + po);
+        }
       }
     }
     // release the last update of the round

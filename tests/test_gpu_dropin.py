@@ -75,3 +75,49 @@ def test_spr_search(tmp_path):
     a, out = run(B200, str(tmp_path), args, {"PLK_SHIM_VERBOSE": "1"})
     b, _ = run(REF, str(tmp_path), args)
     assert abs(a - b) <= 1e-5 * abs(b), (a, b)
+
+
+def _supports(tmp, phy):
+    """Branch supports (internal-node labels) of the tree PhyML wrote next to the alignment."""
+    txt = open(os.path.join(tmp, phy + "_phyml_tree.txt")).read()
+    return [float(x) for x in re.findall(r"\)([0-9.eE+-]+):", txt)]
+
+
+@needs_bins
+@pytest.mark.parametrize("bflag", [None, "-4", "-2"])
+def test_branch_supports_match_reference(tmp_path, bflag):
+    """aLRT-type branch supports (alrt.c:172): default aBayes (no -b: init.c:604), SH-like (-b -4) and
+    Chi2-based aLRT (-b -2).  NNI_Neigh_BL reads tree->c_lnL_sorted right after edge-level Lk() calls
+    (alrt.c:453,555,682): the binding mirrors it after every Lk(b) while aLRT() runs.  Supports must match the
+    CPU run's."""
+    phy, nwk = stage(tmp_path, "synth_dna_deep")
+    lines = open(os.path.join(str(tmp_path), phy)).read().splitlines()
+    n_sites = lines[0].split()[1]
+    for name in ("a.phy", "b.phy"):
+        with open(os.path.join(str(tmp_path), name), "w") as f:
+            f.write(f"16 {n_sites}\n" + "\n".join(lines[1:17]) + "\n")
+    args = ["-d", "nt", "-m", "HKY85", "-c", "4", "-a", "0.5", "-f", "e", "-o", "lr", "--r_seed", "1", "--no_memory_check"]
+    if bflag is not None:
+        args += ["-b", bflag]
+    a, _ = run(B200, str(tmp_path), ["-i", "a.phy"] + args)
+    b, _ = run(REF, str(tmp_path), ["-i", "b.phy"] + args)
+    assert abs(a - b) <= 1e-6 * abs(b), (a, b)
+    sa, sb = _supports(str(tmp_path), "a.phy"), _supports(str(tmp_path), "b.phy")
+    assert len(sa) == len(sb) and len(sa) >= 10
+    for x, y in zip(sa, sb):
+        assert abs(x - y) <= 2e-3 * max(1.0, abs(y)), (sa, sb)
+
+
+@needs_bins
+def test_bootstrap_replicates_are_refused(tmp_path):
+    """-b N (N > 0): replicate trees share the main tree's likelihood structures (utilities.c:4042) and have no
+    device instance; the binding must refuse loudly instead of silently running the CPU code."""
+    phy, nwk = stage(tmp_path, "synth_dna_deep")
+    lines = open(os.path.join(str(tmp_path), phy)).read().splitlines()
+    n_sites = lines[0].split()[1]
+    with open(os.path.join(str(tmp_path), "a.phy"), "w") as f:
+        f.write(f"8 {n_sites}\n" + "\n".join(lines[1:9]) + "\n")
+    res = subprocess.run([B200, "-i", "a.phy", "-d", "nt", "-m", "HKY85", "-c", "4", "-o", "n", "-b", "2", "--r_seed", "1",
+                          "--no_memory_check"], cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
+    assert res.returncode != 0
+    assert "without a device instance" in (res.stdout + res.stderr)

@@ -1,7 +1,4 @@
 mkdir -p gpurun_out
-nvidia-smi -L > gpurun_out/r2h_gpus.txt
-for N in 8 4; do
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r2h_bench_n$N.json 2> gpurun_out/r2h_bench_n$N.err
-done
-PLK_COMM=nccl python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/r2h_bench_n8_nccl.json 2> gpurun_out/r2h_bench_n8_nccl.err
-python -m pytest tests/test_gpu_multi.py -q 2>&1 | tail -5 > gpurun_out/r2h_pytest_multi.log
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_big_configs.py -x -q -k "aa or proteic or lg or synthetic or AA" 2>&1 | tail -3 > gpurun_out/r2l_pytest.log
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-secondary --workload aa_200x50k > gpurun_out/r2l_aa3.json 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'k_traverse_aa' -s 2 -c 1 -f -o gpurun_out/prof_aa3c python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-secondary --workload aa_200x50k > gpurun_out/ncu_aa3c.log 2>&1
