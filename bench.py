@@ -114,13 +114,17 @@ def load_peaks():
 
 def k1_kernel_name(ns, ncatg):
     if ns == 4 and ncatg in (1, 2, 4, 8):
-        v = os.environ.get("PLK_T2_VARIANT")
+        v = int(os.environ.get("PLK_T2_VARIANT", "20"))
         if os.environ.get("PLK_TRAV_V1", "0") not in ("", "0"):
             return "k_traverse_dna<%d,2>" % ncatg
-        if v is not None and int(v) < 10:
+        if v < 10:
             return "k_traverse_dna2<%d>" % ncatg
-        return "k_traverse_dna3<%d> (DMMA.8x8x4)" % ncatg
+        if v < 20:
+            return "k_traverse_dna3<%d> (DMMA.8x8x4)" % ncatg
+        return "k_traverse_dna4<%d,15> (DMMA.8x8x4)" % ncatg
     if ns == 20:
+        if ncatg in (1, 2, 4, 8) and os.environ.get("PLK_AA_V1", "0") in ("", "0"):
+            return "k_traverse_aa3<%d> (DMMA.8x8x4)" % ncatg
         return "k_traverse_aa (DMMA.8x8x4)"
     return "k_partial_generic"
 
@@ -172,12 +176,10 @@ def measure(name, rank, world, local, steps, warmup, e2e=True, clocks=True, proc
         eng.set_weights_ptr(h_wght.data_ptr(), h_invar.data_ptr())
         eng.set_model(m)
 
-    def evaluate():
-        eng.update_pmats(edges, lengths)                      # K0, all edges (lk.c:500-505)
-        # K1 + K2: post-order traversal (lk.c:562) and the site loop at the root edge (lk.c:578-645) as one engine
-        # call; for 4-state / 4-category data the edge reduction (+ the cross-GPU sum when sharded) is the
-        # epilogue of the traversal kernel, i.e. one launch
-        return eng.traverse_edge_lnl(ops_packed, left, rght, tree.root_edge)
+    # one step = Lk(NULL): K0 for all edges (lk.c:500-505), post-order traversal (lk.c:562) and the site loop at the
+    # root edge (lk.c:578-645) through ONE C-ABI call (plk_lk_full); for 4-state / 4-category data the edge reduction
+    # (+ the cross-GPU sum when sharded) is the epilogue of the traversal kernel: two launches per step
+    evaluate = eng.lk_full_call(edges, lengths, ops_packed, left, rght, tree.root_edge)
 
     eng.set_tip_table(pat.table())
     upload_inputs()

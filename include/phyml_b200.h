@@ -143,6 +143,13 @@ int plk_edge_lnl(plk_instance *inst, plk_side left, plk_side rght, int pmat, dou
 int plk_traverse_edge_lnl(plk_instance *inst, int n_ops, const plk_op *ops, plk_side left,
                           plk_side rght, int pmat, double *lnl, int *numerical_warning);
 
+/* the whole of Lk(NULL) after the host's model update (Update_RAS / Update_Efrq / Update_Eigen,
+ * src/lk.c:489-495) as one call: the P-matrix loop over all edges (src/lk.c:500-505), Post_Order_Lk
+ * (:562-564) and the site loop at the root edge (:578-645) = plk_update_pmats + plk_traverse_edge_lnl. */
+int plk_lk_full(plk_instance *inst, int n_pmat, const int *pmat, const double *lengths, int n_ops,
+                const plk_op *ops, plk_side left, plk_side rght, int edge_pmat, double *lnl,
+                int *numerical_warning);
+
 /* ---- K3: eigen-basis projection -------------------------------------------------------------
  * replaces Update_Eigen_Lr (src/lk.c:1038-1114, src/avx.c:21-105): tree->dot_prod stays on the
  * device; also latches fact_sum_scale = scale(left)+scale(rght) for K4. */

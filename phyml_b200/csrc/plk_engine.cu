@@ -781,6 +781,25 @@ int plk_update_pmats(plk_instance *inst, int n, const int *pmat, const double *l
   const int    per_slot = (int)(kStageBytes / sizeof(PmatJob));
   const int    threads = ((ns * ns + 31) / 32) * 32;
   const size_t smem = (size_t)(kMaxNs + ns * ns) * sizeof(double);
+  if (n <= kPmatInline)
+  {  // job list in the kernel's parameter block: one launch, nothing staged
+    static thread_local PmatJobsInline jobs;
+    jobs.base = inst->d_pmat;
+    jobs.stride = (unsigned)inst->pmat_stride;
+    for (int i = 0; i < n; ++i)
+    {
+      ARG_CHECK(inst, pmat[i] >= 0 && pmat[i] < inst->cfg.n_pmat, "pmat handle out of range");
+      jobs.h[i] = pmat[i];
+      jobs.l[i] = l[i];
+    }
+    if (n > 0)
+    {
+      k_pmat_inline<<<n * nc, threads, smem, inst->stream>>>(jobs, inst->d_model, ns, nc, ns == 4 ? 1 : (ns == 20 ? 2 : 0));
+      inst->launches++;
+      CU_TRY(inst, cudaGetLastError());
+    }
+    return PLK_OK;
+  }
   for (int off = 0; off < n; off += per_slot)
   {
     const int             cnt = std::min(per_slot, n - off);
@@ -957,9 +976,9 @@ static int launch_traverse_aa(plk_instance *inst, const OpDev *d_ops, int n_ops)
   if (tile_sites > kAaTileCap) tile_sites = kAaTileCap;
   n_tiles = (P + tile_sites - 1) / tile_sites;
   const int       grid = std::min(n_tiles, slots);
-  const long long code_delta = (long long)(inst->d_tipcodes - inst->d_tiprows);
   k_traverse_aa<<<grid, kAaThreads, smem, inst->stream>>>(d_ops, n_ops, P, nc, tile_sites, n_tiles, inst->d_wght,
-                                                          inst->d_tipmask, code_delta, inst->apply_scaling);
+                                                          inst->d_tipmask, inst->d_tiprows, inst->d_tipcodes,
+                                                          inst->apply_scaling);
   inst->launches++;
   CU_TRY(inst, cudaGetLastError());
   return PLK_OK;
@@ -1546,6 +1565,16 @@ int plk_traverse_edge_lnl(plk_instance *inst, int n_ops, const plk_op *ops, plk_
   const int rc = traverse_edge_launch(inst, n_ops, ops, left, rght, pmat);
   if (rc) return rc;
   return finish_reduction(inst, lnl, nullptr, warn);
+}
+
+// Lk(NULL) after the host's model update as ONE call: the P-matrix loop (lk.c:500-505), Post_Order_Lk (:562-564)
+// and the site loop at the root edge (:578-645): two launches for 4-state / 4-category data (K0, fused K1 + K2)
+int plk_lk_full(plk_instance *inst, int n_pmat, const int *pmat, const double *l, int n_ops, const plk_op *ops,
+                plk_side left, plk_side rght, int edge_pmat, double *lnl, int *warn)
+{
+  const int rc = plk_update_pmats(inst, n_pmat, pmat, l);
+  if (rc) return rc;
+  return plk_traverse_edge_lnl(inst, n_ops, ops, left, rght, edge_pmat, lnl, warn);
 }
 
 // ---- K3 ------------------------------------------------------------------------------------------

@@ -194,19 +194,18 @@ struct PmatJob
   double  l;  // b->l->v
 };
 
-__global__ void k_pmat(const PmatJob *__restrict__ jobs, const ModelDev *__restrict__ mod, int ns, int ncatg,
-                       int with_tip_table)
+__device__ __forceinline__ void pmat_body(double *__restrict__ Pout, double l, const ModelDev *__restrict__ mod, int ns,
+                                          int ncatg, int with_tip_table)
 {
   extern __shared__ double sm[];  // expt[ns] | raw / normalised P of this category: [ns*ns]
   double *expt = sm;
   double *raw = sm + kMaxNs;
-  const int job = blockIdx.x / ncatg;
   const int c = blockIdx.x % ncatg;
   const int e = threadIdx.x;
   const int nn = ns * ns;
 
   // lk.c:2296-2300
-  double len = fmax(0.0, jobs[job].l) * mod->rates[c];
+  double len = fmax(0.0, l) * mod->rates[c];
   len = len * mod->br_len_mult;
   if (len < mod->l_min)
     len = mod->l_min;
@@ -231,7 +230,7 @@ __global__ void k_pmat(const PmatJob *__restrict__ jobs, const ModelDev *__restr
     double    sum = 0.0;
     for (int j = 0; j < ns; ++j) sum = sum + raw[i * ns + j];  // models.c:296-297
     pn = raw[e] / sum;                                          // models.c:298
-    jobs[job].P[(size_t)c * nn + e] = pn;
+    Pout[(size_t)c * nn + e] = pn;
   }
   if (with_tip_table == 2)
   {  // ns == 20: tPx[c][s][i] = P[c][i][s] for s < 20 (what an unambiguous tip in state s contributes) and
@@ -239,7 +238,7 @@ __global__ void k_pmat(const PmatJob *__restrict__ jobs, const ModelDev *__restr
     __syncthreads();
     if (e < nn) raw[e] = pn;
     __syncthreads();
-    double *TX = jobs[job].P + (size_t)ncatg * nn + (size_t)c * 420;
+    double *TX = Pout + (size_t)ncatg * nn + (size_t)c * 420;
     if (e < nn) TX[(e % ns) * ns + (e / ns)] = pn;
     if (e < ns)
     {
@@ -249,7 +248,7 @@ __global__ void k_pmat(const PmatJob *__restrict__ jobs, const ModelDev *__restr
     }
     // Pf[c][j = n*5+kk][lane = g*4+t] = P[c][8n+g][4kk+t] (0 for rows >= 20): the B fragments of
     // k_traverse_aa in the order its lanes read them (conflict-free LDS.64, no address arithmetic)
-    double *PF = jobs[job].P + (size_t)ncatg * (nn + 420) + (size_t)c * 480;
+    double *PF = Pout + (size_t)ncatg * (nn + 420) + (size_t)c * 480;
     for (int q = e; q < 480; q += blockDim.x)
     {
       const int j = q >> 5, ln = q & 31, n = j / 5, kk = j % 5, gg = ln >> 2, tt = ln & 3;
@@ -261,7 +260,7 @@ __global__ void k_pmat(const PmatJob *__restrict__ jobs, const ModelDev *__restr
     __syncthreads();
     if (e < nn) raw[e] = pn;
     __syncthreads();
-    double *TP = jobs[job].P + (size_t)ncatg * nn + (size_t)c * 64;
+    double *TP = Pout + (size_t)ncatg * nn + (size_t)c * 64;
     for (int t = e; t < 64; t += blockDim.x)
     {
       const int m = t >> 2, i = t & 3;
@@ -272,6 +271,30 @@ __global__ void k_pmat(const PmatJob *__restrict__ jobs, const ModelDev *__restr
       TP[tip_row4(m) * 4 + i] = a;
     }
   }
+}
+
+__global__ void k_pmat(const PmatJob *__restrict__ jobs, const ModelDev *__restrict__ mod, int ns, int ncatg,
+                       int with_tip_table)
+{
+  const int job = blockIdx.x / ncatg;
+  pmat_body(jobs[job].P, jobs[job].l, mod, ns, ncatg, with_tip_table);
+}
+
+// the same with the job list in the kernel's parameter block (no staging copy in front of the launch): up to
+// kPmatInline matrices, the common case of one full-tree evaluation (2n - 3 edges)
+constexpr int kPmatInline = 1024;
+struct PmatJobsInline
+{
+  double *base;               // P-matrix record 0
+  unsigned stride;            // doubles between records
+  int     h[kPmatInline];     // record index
+  double  l[kPmatInline];     // branch length
+};
+__global__ void k_pmat_inline(const __grid_constant__ PmatJobsInline jobs, const ModelDev *__restrict__ mod, int ns,
+                              int ncatg, int with_tip_table)
+{
+  const int job = blockIdx.x / ncatg;
+  pmat_body(jobs.base + (size_t)jobs.h[job] * jobs.stride, jobs.l[job], mod, ns, ncatg, with_tip_table);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1759,10 +1782,34 @@ __device__ __forceinline__ void aa_tip_frag(const double *tpx /* [21][20] of thi
   }
 }
 
+// general ambiguity code (rare): only instantiated in the non-unrolled copy of the category loop of k_traverse_aa3.  `tpx_a` = shared-memory address of tPx[21][20] of the category.
+__device__ __forceinline__ void aa_tip_frag_general(uint32_t tpx_a, uint32_t mask, int t, double (&cf)[6])
+{
+#pragma unroll
+  for (int n = 0; n < 3; ++n)
+  {
+    const int i0 = n * 8 + 2 * t;
+    double    a0 = 0.0, a1 = 0.0;
+    bool      first = true;
+    if (i0 < 20)
+      for (int j = 0; j < 20; ++j)
+        if ((mask >> j) & 1u)
+        {  // ascending-j sum of the selected columns (same order as the reference)
+          double x, y;
+          lds128(tpx_a + (uint32_t)(j * 20 + i0) * 8, x, y);
+          a0 = first ? x : a0 + x;
+          a1 = first ? y : a1 + y;
+          first = false;
+        }
+    cf[2 * n] = a0;
+    cf[2 * n + 1] = a1;
+  }
+}
+
 __global__ void __launch_bounds__(kAaThreads, 1)
     k_traverse_aa(const OpDev *__restrict__ ops, int n_ops, int npat, int ncatg, int tile_sites, int n_tiles,
-                  const double *__restrict__ wght, const uint32_t *__restrict__ tipmask, long long code_delta,
-                  int apply_scaling)
+                  const double *__restrict__ wght, const uint32_t *__restrict__ tipmask,
+                  const uint8_t *__restrict__ rows_base, const uint8_t *__restrict__ codes_base, int apply_scaling)
 {
   constexpr int                      S = kAaStages;
   extern __shared__ __align__(128) unsigned char aa_smem[];
@@ -1868,14 +1915,14 @@ __global__ void __launch_bounds__(kAaThreads, 1)
         if (tip1)
         {
           row1[u] = op.t1[site[u]];
-          if (row1[u] > 20) msk1[u] = tipmask[(op.t1 + code_delta)[site[u]]] & 0xFFFFFu;
+          if (row1[u] > 20) msk1[u] = tipmask[codes_base[(op.t1 - rows_base) + site[u]]] & 0xFFFFFu;
         }
         else
           sc[u] += op.s1[site[u]];
         if (tip2)
         {
           row2[u] = op.t2[site[u]];
-          if (row2[u] > 20) msk2[u] = tipmask[(op.t2 + code_delta)[site[u]]] & 0xFFFFFu;
+          if (row2[u] > 20) msk2[u] = tipmask[codes_base[(op.t2 - rows_base) + site[u]]] & 0xFFFFFu;
         }
         else
           sc[u] += op.s2[site[u]];
@@ -2054,6 +2101,147 @@ struct __align__(128) Aa3Stage
   uint8_t rows[2][kAaTileCap + 24];    // per tip child: tip-table rows of the tile's sites (+ alignment slack)
 };
 
+// the category loop of one k_traverse_aa3 item: products, stores, running per-site maximum (returned as the
+// largest exponent word).  GEN = a general ambiguity code is present at some lane (rare): not unrolled.
+template <int NCATG, bool GEN>
+__device__ __forceinline__ int aa3_categories(const double *a1p, const double *a2p, double *outp, uint32_t M1a, uint32_t M2a,
+                                              bool tip1, bool tip2, int row1, int row2, uint32_t msk1, uint32_t msk2,
+                                              bool live, int lane)
+{
+  const int t = lane & 3;
+    int hm = 0;
+          // software pipeline over the categories: the A fragments of category c + 1 are in flight while c is multiplied
+          double a1n[5], a2n[5];
+  #pragma unroll
+          for (int kk = 0; kk < 5; ++kk) a1n[kk] = a2n[kk] = 0.0;
+          if (!tip1)
+          {
+  #pragma unroll
+            for (int kk = 0; kk < 5; ++kk) a1n[kk] = ldg64q(a1p + kk * 32);
+          }
+          if (!tip2)
+          {
+  #pragma unroll
+            for (int kk = 0; kk < 5; ++kk) a2n[kk] = ldg64q(a2p + kk * 32);
+          }
+          auto one_category = [&](const int c) {
+            double a1[5], a2[5], cf1[6], cf2[6];
+            bool   f1, f2;  // all-ones filters (avx.c:575-587)
+  #pragma unroll
+            for (int kk = 0; kk < 5; ++kk)
+            {
+              a1[kk] = a1n[kk];
+              a2[kk] = a2n[kk];
+            }
+            if (c + 1 < NCATG)
+            {
+              if (!tip1)
+              {
+  #pragma unroll
+                for (int kk = 0; kk < 5; ++kk) a1n[kk] = ldg64q(a1p + (c + 1) * 160 + kk * 32);
+              }
+              if (!tip2)
+              {
+  #pragma unroll
+                for (int kk = 0; kk < 5; ++kk) a2n[kk] = ldg64q(a2p + (c + 1) * 160 + kk * 32);
+              }
+            }
+            if (!tip1)
+            {
+              const uint32_t Pf = M1a + (uint32_t)(c * 480 + lane) * 8;
+  #pragma unroll
+              for (int q = 0; q < 6; ++q) cf1[q] = 0.0;
+              // k outermost: the three n-tile accumulators advance together (independent MMA chains)
+  #pragma unroll
+              for (int kk = 0; kk < 5; ++kk)
+  #pragma unroll
+                for (int n = 0; n < 3; ++n) dmma884(cf1[2 * n], cf1[2 * n + 1], a1[kk], lds64(Pf + (n * 5 + kk) * 256));
+              f1 = __double2hiint(a1[0]) == 0x3FF00000;
+            }
+            else
+            {
+              if (row1 <= 20)
+              {
+                const uint32_t T = M1a + (uint32_t)(c * 420 + row1 * 20 + 2 * t) * 8;
+                lds128(T, cf1[0], cf1[1]);
+                lds128(T + 64, cf1[2], cf1[3]);
+                cf1[4] = cf1[5] = 0.0;
+                if (t < 2) lds128(T + 128, cf1[4], cf1[5]);
+              }
+              else if constexpr (GEN)
+                aa_tip_frag_general(M1a + (uint32_t)(c * 420) * 8, msk1, t, cf1);
+              f1 = (row1 == 20);
+            }
+            if (!tip2)
+            {
+              const uint32_t Pf = M2a + (uint32_t)(c * 480 + lane) * 8;
+  #pragma unroll
+              for (int q = 0; q < 6; ++q) cf2[q] = 0.0;
+  #pragma unroll
+              for (int kk = 0; kk < 5; ++kk)
+  #pragma unroll
+                for (int n = 0; n < 3; ++n) dmma884(cf2[2 * n], cf2[2 * n + 1], a2[kk], lds64(Pf + (n * 5 + kk) * 256));
+              f2 = __double2hiint(a2[0]) == 0x3FF00000;
+            }
+            else
+            {
+              if (row2 <= 20)
+              {
+                const uint32_t T = M2a + (uint32_t)(c * 420 + row2 * 20 + 2 * t) * 8;
+                lds128(T, cf2[0], cf2[1]);
+                lds128(T + 64, cf2[2], cf2[3]);
+                cf2[4] = cf2[5] = 0.0;
+                if (t < 2) lds128(T + 128, cf2[4], cf2[5]);
+              }
+              else if constexpr (GEN)
+                aa_tip_frag_general(M2a + (uint32_t)(c * 420) * 8, msk2, t, cf2);
+              f2 = (row2 == 20);
+            }
+            double o[6];
+  #pragma unroll
+            for (int q = 0; q < 6; ++q) o[q] = cf1[q] * cf2[q];
+            if (__any_sync(0xffffffffu, f1 && f2))
+            {  // exact test: all 20 states of both children are 1.0 at this (site, category)
+              bool one1 = f1, one2 = f2;
+              if (!tip1)
+              {
+                const bool mine = (a1[0] == 1.0) && (a1[1] == 1.0) && (a1[2] == 1.0) && (a1[3] == 1.0) && (a1[4] == 1.0);
+                one1 = ((__ballot_sync(0xffffffffu, mine) >> (lane & ~3)) & 0xFu) == 0xFu;
+              }
+              if (!tip2)
+              {
+                const bool mine = (a2[0] == 1.0) && (a2[1] == 1.0) && (a2[2] == 1.0) && (a2[3] == 1.0) && (a2[4] == 1.0);
+                one2 = ((__ballot_sync(0xffffffffu, mine) >> (lane & ~3)) & 0xFu) == 0xFu;
+              }
+              if (one1 && one2)
+              {
+  #pragma unroll
+                for (int q = 0; q < 6; ++q) o[q] = 1.0;
+              }
+            }
+            // states n*8 + 2t, +1: the third n-tile only holds states 16..19 (t < 2)
+            hm = max(hm, max(max(__double2hiint(o[0]), __double2hiint(o[1])), max(__double2hiint(o[2]), __double2hiint(o[3]))));
+            if (t < 2) hm = max(hm, max(__double2hiint(o[4]), __double2hiint(o[5])));
+            if (live)
+            {
+              stg128q(outp + c * 160, o[0], o[1]);
+              stg128q(outp + c * 160 + 64, o[2], o[3]);
+              if (t < 2) stg128q(outp + c * 160 + 128, o[4], o[5]);
+            }
+          };
+          if constexpr (GEN)
+          {
+#pragma unroll 1
+            for (int c = 0; c < NCATG; ++c) one_category(c);
+          }
+          else
+          {
+#pragma unroll
+            for (int c = 0; c < NCATG; ++c) one_category(c);
+          }
+  return hm;
+}
+
 template <int NCATG>
 __global__ void __launch_bounds__(kAaThreads, 1)
     k_traverse_aa3(const OpDev *__restrict__ ops, int n_ops, int npat, int tile_sites, int n_tiles,
@@ -2186,128 +2374,12 @@ __global__ void __launch_bounds__(kAaThreads, 1)
         else
           sc += ldg32q(reinterpret_cast<const int *>(lds_ptr(sa + kT4OffS2)) + site);
 
-        int hm = 0;
-        // software pipeline over the categories: the A fragments of category c + 1 are in flight while c is multiplied
-        double a1n[5], a2n[5];
-#pragma unroll
-        for (int kk = 0; kk < 5; ++kk) a1n[kk] = a2n[kk] = 0.0;
-        if (!tip1)
-        {
-#pragma unroll
-          for (int kk = 0; kk < 5; ++kk) a1n[kk] = ldg64q(a1p + kk * 32);
-        }
-        if (!tip2)
-        {
-#pragma unroll
-          for (int kk = 0; kk < 5; ++kk) a2n[kk] = ldg64q(a2p + kk * 32);
-        }
-#pragma unroll
-        for (int c = 0; c < NCATG; ++c)
-        {
-          double a1[5], a2[5], cf1[6], cf2[6];
-          bool   f1, f2;  // all-ones filters (avx.c:575-587)
-#pragma unroll
-          for (int kk = 0; kk < 5; ++kk)
-          {
-            a1[kk] = a1n[kk];
-            a2[kk] = a2n[kk];
-          }
-          if (c + 1 < NCATG)
-          {
-            if (!tip1)
-            {
-#pragma unroll
-              for (int kk = 0; kk < 5; ++kk) a1n[kk] = ldg64q(a1p + (c + 1) * 160 + kk * 32);
-            }
-            if (!tip2)
-            {
-#pragma unroll
-              for (int kk = 0; kk < 5; ++kk) a2n[kk] = ldg64q(a2p + (c + 1) * 160 + kk * 32);
-            }
-          }
-          if (!tip1)
-          {
-            const uint32_t Pf = M1a + (uint32_t)(c * 480 + lane) * 8;
-#pragma unroll
-            for (int q = 0; q < 6; ++q) cf1[q] = 0.0;
-            // k outermost: the three n-tile accumulators advance together (independent MMA chains)
-#pragma unroll
-            for (int kk = 0; kk < 5; ++kk)
-#pragma unroll
-              for (int n = 0; n < 3; ++n) dmma884(cf1[2 * n], cf1[2 * n + 1], a1[kk], lds64(Pf + (n * 5 + kk) * 256));
-            f1 = __double2hiint(a1[0]) == 0x3FF00000;
-          }
-          else
-          {
-            if (row1 <= 20)
-            {
-              const uint32_t T = M1a + (uint32_t)(c * 420 + row1 * 20 + 2 * t) * 8;
-              lds128(T, cf1[0], cf1[1]);
-              lds128(T + 64, cf1[2], cf1[3]);
-              cf1[4] = cf1[5] = 0.0;
-              if (t < 2) lds128(T + 128, cf1[4], cf1[5]);
-            }
-            else
-              aa_tip_frag(reinterpret_cast<const double *>(&st[s].M[0][c * 420]), row1, msk1, t, cf1);
-            f1 = (row1 == 20);
-          }
-          if (!tip2)
-          {
-            const uint32_t Pf = M2a + (uint32_t)(c * 480 + lane) * 8;
-#pragma unroll
-            for (int q = 0; q < 6; ++q) cf2[q] = 0.0;
-#pragma unroll
-            for (int kk = 0; kk < 5; ++kk)
-#pragma unroll
-              for (int n = 0; n < 3; ++n) dmma884(cf2[2 * n], cf2[2 * n + 1], a2[kk], lds64(Pf + (n * 5 + kk) * 256));
-            f2 = __double2hiint(a2[0]) == 0x3FF00000;
-          }
-          else
-          {
-            if (row2 <= 20)
-            {
-              const uint32_t T = M2a + (uint32_t)(c * 420 + row2 * 20 + 2 * t) * 8;
-              lds128(T, cf2[0], cf2[1]);
-              lds128(T + 64, cf2[2], cf2[3]);
-              cf2[4] = cf2[5] = 0.0;
-              if (t < 2) lds128(T + 128, cf2[4], cf2[5]);
-            }
-            else
-              aa_tip_frag(reinterpret_cast<const double *>(&st[s].M[1][c * 420]), row2, msk2, t, cf2);
-            f2 = (row2 == 20);
-          }
-          double o[6];
-#pragma unroll
-          for (int q = 0; q < 6; ++q) o[q] = cf1[q] * cf2[q];
-          if (__any_sync(0xffffffffu, f1 && f2))
-          {  // exact test: all 20 states of both children are 1.0 at this (site, category)
-            bool one1 = f1, one2 = f2;
-            if (!tip1)
-            {
-              const bool mine = (a1[0] == 1.0) && (a1[1] == 1.0) && (a1[2] == 1.0) && (a1[3] == 1.0) && (a1[4] == 1.0);
-              one1 = ((__ballot_sync(0xffffffffu, mine) >> (lane & ~3)) & 0xFu) == 0xFu;
-            }
-            if (!tip2)
-            {
-              const bool mine = (a2[0] == 1.0) && (a2[1] == 1.0) && (a2[2] == 1.0) && (a2[3] == 1.0) && (a2[4] == 1.0);
-              one2 = ((__ballot_sync(0xffffffffu, mine) >> (lane & ~3)) & 0xFu) == 0xFu;
-            }
-            if (one1 && one2)
-            {
-#pragma unroll
-              for (int q = 0; q < 6; ++q) o[q] = 1.0;
-            }
-          }
-          // states n*8 + 2t, +1: the third n-tile only holds states 16..19 (t < 2)
-          hm = max(hm, max(max(__double2hiint(o[0]), __double2hiint(o[1])), max(__double2hiint(o[2]), __double2hiint(o[3]))));
-          if (t < 2) hm = max(hm, max(__double2hiint(o[4]), __double2hiint(o[5])));
-          if (live)
-          {
-            stg128q(outp + c * 160, o[0], o[1]);
-            stg128q(outp + c * 160 + 64, o[2], o[3]);
-            if (t < 2) stg128q(outp + c * 160 + 128, o[4], o[5]);
-          }
-        }
+        // general ambiguity codes (rare) take a copy of the category loop that is not unrolled: inlined into the
+        // unrolled loop their code (2 children x NCATG copies) quadrupled the kernel
+        const bool gen = __any_sync(0xffffffffu, (tip1 && row1 > 20) || (tip2 && row2 > 20));
+        const int  hm0 = gen ? aa3_categories<NCATG, true>(a1p, a2p, outp, M1a, M2a, tip1, tip2, row1, row2, msk1, msk2, live, lane)
+                             : aa3_categories<NCATG, false>(a1p, a2p, outp, M1a, M2a, tip1, tip2, row1, row2, msk1, msk2, live, lane);
+        int        hm = hm0;
         // ---- per-site maximum over all categories and states (exponent words: all entries >= 0; NaN counts as
         // large like the reference), rescaling (avx.c:498-510)
         hm = max(hm, __shfl_xor_sync(0xffffffffu, hm, 1));

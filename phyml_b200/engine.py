@@ -42,7 +42,7 @@ assert OP_DTYPE.itemsize == C.sizeof(_Op)
 EXPORTS = [
     "plk_create", "plk_destroy", "plk_last_error", "plk_sync", "plk_set_pattern_weights",
     "plk_set_tip_table", "plk_set_tip_codes", "plk_set_all_tip_codes", "plk_set_all_tip_codes_packed4", "plk_set_tip_vectors", "plk_set_model", "plk_update_pmats",
-    "plk_set_pmat", "plk_get_pmat", "plk_update_partials", "plk_edge_lnl", "plk_traverse_edge_lnl", "plk_eigen_lr",
+    "plk_set_pmat", "plk_get_pmat", "plk_update_partials", "plk_edge_lnl", "plk_traverse_edge_lnl", "plk_lk_full", "plk_eigen_lr",
     "plk_edge_lnl_dlnl", "plk_edge_lnl_eigen", "plk_get_clv", "plk_set_clv", "plk_get_site_lnl",
     "plk_get_dot_prod", "plk_comm_unique_id", "plk_comm_init", "plk_comm_set_allreduce",
     "plk_comm_p2p_export", "plk_comm_p2p_init", "plk_create_sharded", "plk_n_shards",
@@ -84,6 +84,7 @@ def load_library() -> C.CDLL:
     lib.plk_update_partials.argtypes = [vp, C.c_int, vp]
     lib.plk_edge_lnl.argtypes = [vp, _Side, _Side, C.c_int, dp, ip]
     lib.plk_traverse_edge_lnl.argtypes = [vp, C.c_int, vp, _Side, _Side, C.c_int, dp, ip]
+    lib.plk_lk_full.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, _Side, _Side, C.c_int, dp, ip]
     lib.plk_eigen_lr.argtypes = [vp, _Side, _Side]
     lib.plk_edge_lnl_dlnl.argtypes = [vp, dp, dp, dp, ip]
     lib.plk_edge_lnl_eigen.argtypes = [vp, C.c_double, dp, ip]
@@ -286,6 +287,25 @@ class Engine:
                                                 C.byref(out), C.byref(warn)))
         self.numerical_warning = warn.value
         return out.value
+
+    def lk_full_call(self, handles, lengths, ops, left: Side, rght: Side, pmat: int):
+        """Bind the arguments of ``plk_lk_full`` once (arrays are kept alive by the closure, ``lengths`` may be
+        edited in place between calls) and return a zero-argument callable: one full-tree evaluation per call
+        = all P-matrices + Post_Order_Lk + the site loop at the root edge."""
+        h = np.ascontiguousarray(handles, dtype=np.int32)
+        l = np.ascontiguousarray(lengths, dtype=np.float64)
+        arr = ops if isinstance(ops, np.ndarray) else pack_ops(ops)
+        out, warn = C.c_double(0.0), C.c_int(0)
+        args = (self.h, len(h), _ptr(h), _ptr(l), len(arr), _ptr(arr), _Side(left.tip, left.clv), _Side(rght.tip, rght.clv),
+                pmat, C.byref(out), C.byref(warn))
+        fn, ck = self.lib.plk_lk_full, self._ck
+
+        def call(_keep=(h, l, arr)):
+            ck(fn(*args))
+            self.numerical_warning = warn.value
+            return out.value
+
+        return call
 
     # ------------------------------------------------------------------ K3 / K4
     def eigen_lr(self, left: Side, rght: Side):
