@@ -200,6 +200,39 @@ int plk_comm_set_allreduce(plk_instance *inst, int enable);
 int plk_create_sharded(const plk_config *cfg, int n_gpus, const int *devices, plk_instance **out);
 int plk_n_shards(const plk_instance *inst);
 
+/* ---- parsimony: the SPR pre-filter (src/pars.c) ----------------------
+ * Every edge side owns a parsimony buffer (b->ui_l/pars_l/p_pars_l and ..._r, src/make.c:455-475; the host
+ * swaps the three pointers together in Prune_Subtree/Graft_Subtree, src/utilities.c:6268-6278), named here by
+ * an integer handle.  A buffer holds the Fitch state set `ui` (bit j = state j) and step count `pars` per
+ * pattern and, for the step-matrix variant (`general_pars`, src/init.c:777), p_pars[pattern][state].
+ * Tip buffers are uploaded once (Init_Ui_Tips / Init_Partial_Pars_Tips, src/pars.c:111-233).  All results are
+ * integers and bit-identical to the reference's. */
+typedef struct plk_pars_op
+{
+  int dst; /* buffer written: ui/pars (or p_pars) of b_fcus on n's side (src/pars.c:271-351) */
+  int c1;  /* far-end buffers of the two other edges of n */
+  int c2;
+} plk_pars_op;
+/* allocate the handle table; step_mat = tree->step_mat [ns][ns] (Get_Step_Mat, src/pars.c:498) or NULL when
+ * only Fitch parsimony is used.  Replaces Make_Tree_For_Pars' buffers (src/make.c:334-372) on the device. */
+int plk_pars_create(plk_instance *inst, int n_buffers, const int *step_mat);
+/* upload / read back one buffer (host layouts of the reference: int[n_patterns], p_pars int[n_patterns][ns]);
+ * ui and pars go together, p_pars may be NULL (and vice versa). */
+int plk_pars_set_buffer(plk_instance *inst, int buf, const int *ui, const int *pars, const int *p_pars);
+int plk_pars_get_buffer(plk_instance *inst, int buf, int *ui, int *pars, int *p_pars);
+/* replaces Update_Partial_Pars (src/pars.c:239-391) for a dependency-ordered list of updates (the order of
+ * Post_Order_Pars / Pre_Order_Pars, src/pars.c:56-93) in ONE launch.  general != 0: the step-matrix branch. */
+int plk_pars_update(plk_instance *inst, int general, int n_ops, const plk_pars_op *ops);
+/* replaces the site loop of Pars (src/pars.c:40-48) + Pars_Core (src/pars.c:397-439) at the edge whose two
+ * sides are `left` and `rght`: *c_pars = tree->c_pars (THIS instance's patterns), site_pars stays on the device. */
+int plk_pars_edge(plk_instance *inst, int general, int left, int rght, int *c_pars);
+/* the updates and the site loop in one launch: the whole of Pars(NULL) (n - 2 or 3n - 6 updates), or the one
+ * update + Pars(b) of an SPR candidate scored by parsimony (src/spr.c:636-640). */
+int plk_pars_traverse_edge(plk_instance *inst, int general, int n_ops, const plk_pars_op *ops, int left, int rght,
+                           int *c_pars);
+/* tree->site_pars of the last plk_pars_edge / plk_pars_traverse_edge */
+int plk_get_site_pars(plk_instance *inst, int *site_pars);
+
 /* ---- introspection ---------------------------------------------------------------------------- */
 /* kernels launched so far by this instance (bench.py's gpu_launches) */
 long long plk_launch_count(const plk_instance *inst);

@@ -11,6 +11,8 @@
  *     Update_Eigen_Lr             src/lk.c:1038   -> plk_eigen_lr
  *     Make_Tree_For_Lk            src/make.c:17   -> original, then plk_create + uploads
  *     Free_Tree_Lk                src/free.c:387  -> plk_destroy, then original
+ *     Pars / Pars_At_Given_Edge   src/pars.c:20,468 -> plk_pars_traverse_edge (queued updates + the site loop, ONE launch)
+ *     Update_Partial_Pars         src/pars.c:239  -> queued plk_pars_op
  *
  * It is linked into an executable together with the UNMODIFIED reference built as a shared library
  * (oracle/_ref/libphyml_ref.so + main.o): definitions in the executable take precedence over the
@@ -61,6 +63,7 @@
 #include "make.h"
 #include "free.h"
 #include "alrt.h"
+#include "pars.h"
 
 #include "../include/phyml_b200.h"
 
@@ -87,6 +90,14 @@ typedef struct
   int           model_valid;
   double       *wght_print;                        /* data->wght as uploaded (bootstrap-style in-place edits) */
   long long     n_lk, n_dlk, n_partial, n_flush, n_pmat;
+  /* parsimony (src/pars.c): buffers keyed by the host pointer ui_l / ui_r (swapped together with pars_* and
+     p_pars_* by Prune_Subtree / Graft_Subtree, src/utilities.c:6268-6278) */
+  slot_t       *pars_map;
+  int           n_pars, pars_cap, pars_created;
+  unsigned char *pars_on_dev[2];                   /* per handle: the device holds the Fitch [0] / step-matrix [1] data */
+  plk_pars_op  *pars_queue;
+  int           n_pars_queue, pars_queue_cap, pars_queue_general;
+  long long     n_pars_calls, n_pars_upd;
   char         *arena;      /* address-space reservation standing in for tree->big_lk_array */
   size_t        arena_bytes, edge_span;
   double        t_create, t_engine; /* wall-clock: instance creation time stamp, seconds spent inside the hooks */
@@ -398,8 +409,10 @@ void Free_Tree_Lk(t_tree *tree)
       PhyML_Printf("\n. phyml_b200: Lk %lld  dLk %lld  Update_Partial_Lk %lld (in %lld launches)  Update_PMat %lld  "
                    "kernels %lld\n",
                    sh->n_lk, sh->n_dlk, sh->n_partial, sh->n_flush, sh->n_pmat, plk_launch_count(sh->inst));
+      if (sh->n_pars_calls)
+        PhyML_Printf(". phyml_b200: Pars %lld  Update_Partial_Pars %lld\n", sh->n_pars_calls, sh->n_pars_upd);
       PhyML_Printf(". phyml_b200: wall-clock since the instance was created %.2f s: %.2f s inside the likelihood hooks "
-                   "(engine + binding), %.2f s in the untouched host code (spr.c, optimiz.c, pars.c, ...)\n",
+                   "(engine + binding), %.2f s in the untouched host code (spr.c, optimiz.c, ...)\n",
                    total, sh->t_engine, total - sh->t_engine);
     }
     plk_destroy(sh->inst);
@@ -410,6 +423,10 @@ void Free_Tree_Lk(t_tree *tree)
     }
     free(sh->clv_map);
     free(sh->pm_map);
+    free(sh->pars_map);
+    free(sh->pars_on_dev[0]);
+    free(sh->pars_on_dev[1]);
+    free(sh->pars_queue);
     free(sh->queue);
     free(sh->model_uv);
     free(sh->wght_print);
@@ -644,4 +661,174 @@ void aLRT(t_tree *tree)
   g_mirror_sites = 1;
   orig(tree);
   g_mirror_sites = 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Parsimony: src/pars.c.  The SPR search scores every regraft position by Fitch parsimony before any  */
+/* likelihood is computed (spr_pars, src/init.c:786; Test_One_Spr_Target src/spr.c:636-640).  The       */
+/* reference's recursions (Post_Order_Pars / Pre_Order_Pars, src/pars.c:56-93) run unchanged and land  */
+/* in Update_Partial_Pars below; updates are queued and executed together with the site loop of Pars   */
+/* as ONE launch.  Device buffers are created lazily: a buffer that the device has never written is     */
+/* uploaded from the host arrays the first time it is read (tips: Init_Ui_Tips, src/pars.c:164).       */
+static void pars_init(shim_t *sh)
+{
+  t_tree *tree = sh->tree;
+  if (sh->pars_created) return;
+  if (!tree->step_mat || !tree->site_pars)
+  {
+    PhyML_Fprintf(stderr, "\n. phyml_b200: parsimony call before Make_Tree_For_Pars\n");
+    Exit("\n");
+  }
+  sh->pars_cap = 8 * tree->n_otu + 16;
+  sh->pars_map = (slot_t *)calloc(sh->map_cap, sizeof(slot_t));
+  sh->pars_on_dev[0] = (unsigned char *)calloc(sh->pars_cap, 1);
+  sh->pars_on_dev[1] = (unsigned char *)calloc(sh->pars_cap, 1);
+  sh->pars_queue_cap = 8 * tree->n_otu + 64;
+  sh->pars_queue = (plk_pars_op *)malloc(sizeof(plk_pars_op) * sh->pars_queue_cap);
+  CK(plk_pars_create(sh->inst, sh->pars_cap, tree->step_mat), sh);
+  sh->pars_created = 1;
+}
+
+static void pars_flush(shim_t *sh)
+{
+  if (sh->n_pars_queue == 0) return;
+  CK(plk_pars_update(sh->inst, sh->pars_queue_general, sh->n_pars_queue, sh->pars_queue), sh);
+  sh->n_pars_queue = 0;
+}
+
+/* src/make.c:334-372, src/free.c:330-353: when the host (re)allocates or frees its parsimony arrays the pointer
+   keys change meaning: forget them, the device buffers are refilled on first sight */
+static void pars_forget(shim_t *sh)
+{
+  if (!sh || !sh->pars_created) return;
+  sh->n_pars_queue = 0;
+  memset(sh->pars_map, 0, sizeof(slot_t) * sh->map_cap);
+  memset(sh->pars_on_dev[0], 0, sh->pars_cap);
+  memset(sh->pars_on_dev[1], 0, sh->pars_cap);
+  sh->n_pars = 0;
+}
+void Make_Tree_For_Pars(t_tree *tree)
+{
+  static void (*orig)(t_tree *) = NULL;
+  if (!orig) orig = (void (*)(t_tree *))dlsym(RTLD_NEXT, "Make_Tree_For_Pars");
+  orig(tree);
+  pars_forget(shim_of(tree));
+}
+void Free_Tree_Pars(t_tree *tree)
+{
+  static void (*orig)(t_tree *) = NULL;
+  if (!orig) orig = (void (*)(t_tree *))dlsym(RTLD_NEXT, "Free_Tree_Pars");
+  pars_forget(shim_of(tree));
+  orig(tree);
+}
+
+/* handle of a buffer that is about to be READ: first sight => the host arrays are the current contents */
+static int pars_src(shim_t *sh, int general, int *ui, int *pars, int *p_pars)
+{
+  const int h = map_get(sh->pars_map, sh->map_cap, ui, &sh->n_pars, sh->pars_cap, "parsimony");
+  if (!sh->pars_on_dev[general][h])
+  {
+    CK(plk_pars_set_buffer(sh->inst, h, general ? NULL : ui, general ? NULL : pars, general ? p_pars : NULL), sh);
+    sh->pars_on_dev[general][h] = 1;
+  }
+  return h;
+}
+
+static int pars_dst(shim_t *sh, int general, int *ui)
+{
+  const int h = map_get(sh->pars_map, sh->map_cap, ui, &sh->n_pars, sh->pars_cap, "parsimony");
+  sh->pars_on_dev[general][h] = 1;
+  return h;
+}
+
+/* src/pars.c:239-391 */
+void Update_Partial_Pars(t_tree *tree, t_edge *b_fcus, t_node *n)
+{
+  shim_t      *sh = shim_of(tree);
+  t_edge      *b1, *b2;
+  plk_pars_op *op;
+  int          general, left;
+  if (!sh) no_instance("Update_Partial_Pars");
+  if (n->tax) return; /* pars.c:268 */
+  HOOK_ENTER();
+  pars_init(sh);
+  general = tree->mod->s_opt->general_pars ? 1 : 0;
+  if (sh->n_pars_queue > 0 && (sh->pars_queue_general != general || sh->n_pars_queue == sh->pars_queue_cap)) pars_flush(sh);
+  sh->pars_queue_general = general;
+  left = (n == b_fcus->left);
+  b1 = n->b[left ? b_fcus->l_v1 : b_fcus->r_v1]; /* pars.c:277-351: the far-end buffers of n's two other edges */
+  b2 = n->b[left ? b_fcus->l_v2 : b_fcus->r_v2];
+  op = &sh->pars_queue[sh->n_pars_queue];
+  op->c1 = (n == b1->left) ? pars_src(sh, general, b1->ui_r, b1->pars_r, b1->p_pars_r)
+                           : pars_src(sh, general, b1->ui_l, b1->pars_l, b1->p_pars_l);
+  op->c2 = (n == b2->left) ? pars_src(sh, general, b2->ui_r, b2->pars_r, b2->p_pars_r)
+                           : pars_src(sh, general, b2->ui_l, b2->pars_l, b2->p_pars_l);
+  op->dst = pars_dst(sh, general, left ? b_fcus->ui_l : b_fcus->ui_r);
+  sh->n_pars_queue++;
+  sh->n_pars_upd++;
+  HOOK_LEAVE(sh);
+}
+
+/* the site loop of Pars / Pars_At_Given_Edge (src/pars.c:39-50,468-484) behind the queued updates */
+static int pars_at_edge(shim_t *sh, t_edge *b)
+{
+  t_tree   *tree = sh->tree;
+  const int general = tree->mod->s_opt->general_pars ? 1 : 0;
+  int       c_pars = 0, hl, hr;
+  pars_init(sh);
+  if (sh->n_pars_queue > 0 && sh->pars_queue_general != general) pars_flush(sh);
+  hl = pars_src(sh, general, b->ui_l, b->pars_l, b->p_pars_l);
+  hr = pars_src(sh, general, b->ui_r, b->pars_r, b->p_pars_r);
+  CK(plk_pars_traverse_edge(sh->inst, general, sh->n_pars_queue, sh->pars_queue, hl, hr, &c_pars), sh);
+  sh->n_pars_queue = 0;
+  sh->n_pars_calls++;
+  if (getenv("PLK_SHIM_SITE_PARS")) CK(plk_get_site_pars(sh->inst, tree->site_pars), sh); /* no host reader needs it */
+  tree->c_pars = c_pars;
+  return c_pars;
+}
+
+/* src/pars.c:20-51 */
+int Pars(t_edge *b, t_tree *tree)
+{
+  shim_t *sh = shim_of(tree);
+  int     c_pars;
+  if (!sh) no_instance("Pars");
+  HOOK_ENTER();
+  if (b == NULL)
+  { /* pars.c:33-39: the reference's own recursions; every visit lands in Update_Partial_Pars above */
+    Post_Order_Pars(tree->a_nodes[0], tree->a_nodes[0]->v[0], tree);
+    if (tree->both_sides == YES) Pre_Order_Pars(tree->a_nodes[0], tree->a_nodes[0]->v[0], tree);
+    b = tree->a_nodes[0]->b[0];
+  }
+  c_pars = pars_at_edge(sh, b);
+  HOOK_LEAVE(sh);
+  return c_pars;
+}
+
+/* src/pars.c:468-484 */
+int Pars_At_Given_Edge(t_edge *b, t_tree *tree)
+{
+  shim_t *sh = shim_of(tree);
+  int     c_pars;
+  if (!sh) no_instance("Pars_At_Given_Edge");
+  HOOK_ENTER();
+  c_pars = pars_at_edge(sh, b);
+  HOOK_LEAVE(sh);
+  return c_pars;
+}
+
+/* src/pars.c:104,443: host-side readers of the per-edge Fitch sets; no caller in the reference */
+void Site_Pars(t_tree *tree)
+{
+  (void)tree;
+  PhyML_Fprintf(stderr, "\n. phyml_b200: Site_Pars() reads host parsimony buffers that live on the device.\n");
+  Exit("\n");
+}
+int One_Pars_Step(t_edge *b, t_tree *tree)
+{
+  (void)b;
+  (void)tree;
+  PhyML_Fprintf(stderr, "\n. phyml_b200: One_Pars_Step() reads host parsimony buffers that live on the device.\n");
+  Exit("\n");
+  return 0;
 }

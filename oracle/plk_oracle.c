@@ -411,3 +411,88 @@ double plk_oracle_lnl_dlnl(int ns, int ncatg, int npat, const double *wght, cons
   if (dlnl_out) *dlnl_out = with_derivative ? dlnL : 0.0;
   return lnL;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* Parsimony: Fitch sets / Sankoff step matrices of src/pars.c.     */
+
+/* pars.c:374-388: pars = pars_v1 + pars_v2; ui = ui_v1 & ui_v2; empty intersection => one more step, union */
+void plk_oracle_pars_update(int npat, int *ui, int *pars, const int *ui_v1, const int *pars_v1,
+                            const int *ui_v2, const int *pars_v2)
+{
+  int s;
+  for (s = 0; s < npat; ++s)
+  {
+    int p = pars_v1[s] + pars_v2[s];
+    int u = ui_v1[s] & ui_v2[s];
+    if (!u)
+    {
+      p++;
+      u = ui_v1[s] | ui_v2[s];
+    }
+    pars[s] = p;
+    ui[s] = u;
+  }
+}
+
+/* pars.c:355-372 (general_pars): p_pars[s][i] = min_j(p_pars_v1[s][j] + step[i][j]) + min_j(p_pars_v2[s][j] + step[i][j]) */
+void plk_oracle_pars_update_general(int ns, int npat, const int *step_mat, int *p_pars, const int *p_pars_v1,
+                                    const int *p_pars_v2)
+{
+  int s, i, j;
+  for (s = 0; s < npat; ++s)
+    for (i = 0; i < ns; ++i)
+    {
+      int m1 = 1000000000, m2 = 1000000000; /* MAX_PARS, utilities.h:366 */
+      for (j = 0; j < ns; ++j)
+      {
+        int v = p_pars_v1[s * ns + j] + step_mat[i * ns + j];
+        if (v < m1) m1 = v;
+      }
+      for (j = 0; j < ns; ++j)
+      {
+        int v = p_pars_v2[s * ns + j] + step_mat[i * ns + j];
+        if (v < m2) m2 = v;
+      }
+      p_pars[s * ns + i] = m1 + m2;
+    }
+}
+
+/* pars.c:20-51 (site loop of Pars) + pars.c:397-439 (Pars_Core).  c_pars is an int that accumulates
+ * int * double products (`tree->c_pars += site_pars * wght`): converted back to int after every site. */
+int plk_oracle_pars_edge(int general, int ns, int npat, const double *wght, const int *step_mat, const int *ui_l,
+                         const int *pars_l, const int *p_pars_l, const int *ui_r, const int *pars_r,
+                         const int *p_pars_r, int *site_pars)
+{
+  int c_pars = 0, s, i, j;
+  for (s = 0; s < npat; ++s)
+  {
+    int sp;
+    if (general)
+    {
+      sp = 1000000000;
+      for (i = 0; i < ns; ++i)
+      {
+        int ml = 1000000000, mr = 1000000000;
+        for (j = 0; j < ns; ++j)
+        {
+          int v = p_pars_l[s * ns + j] + step_mat[i * ns + j];
+          if (v < ml) ml = v;
+        }
+        for (j = 0; j < ns; ++j)
+        {
+          int v = p_pars_r[s * ns + j] + step_mat[i * ns + j];
+          if (v < mr) mr = v;
+        }
+        if (ml + mr < sp) sp = ml + mr;
+      }
+    }
+    else
+    {
+      sp = pars_l[s] + pars_r[s];
+      if (!(ui_l[s] & ui_r[s])) sp++;
+    }
+    if (site_pars) site_pars[s] = sp;
+    c_pars = (int)((double)c_pars + (double)sp * wght[s]);
+  }
+  return c_pars;
+}

@@ -67,6 +67,18 @@ double plk_oracle_lnl_dlnl(int ns, int ncatg, int npat, const double *wght, cons
                            const double *lambda, const double *dot_prod, const int *fact_sum_scale,
                            double *l, int with_derivative, double *dlnl, int *numerical_warning);
 
+/* Parsimony (src/pars.c).  Fitch: ui = state-set bit mask, pars = steps below the node, int[npat] each.
+ * follows pars.c:374-388 (Update_Partial_Pars, Fitch branch). */
+void plk_oracle_pars_update(int npat, int *ui, int *pars, const int *ui_v1, const int *pars_v1,
+                            const int *ui_v2, const int *pars_v2);
+/* follows pars.c:355-372 (general_pars branch): p_pars [npat][ns], step_mat [ns][ns]. */
+void plk_oracle_pars_update_general(int ns, int npat, const int *step_mat, int *p_pars, const int *p_pars_v1,
+                                    const int *p_pars_v2);
+/* follows pars.c:20-51 (site loop of Pars) and pars.c:397-439 (Pars_Core); returns c_pars, fills site_pars. */
+int plk_oracle_pars_edge(int general, int ns, int npat, const double *wght, const int *step_mat, const int *ui_l,
+                         const int *pars_l, const int *p_pars_l, const int *ui_r, const int *pars_r,
+                         const int *p_pars_r, int *site_pars);
+
 #ifdef __cplusplus
 }
 #endif

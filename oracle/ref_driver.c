@@ -18,7 +18,13 @@
  *                 model's eigen system and rates, lnL, pattern weights, per-pattern lnL) -- used by
  *                 tests/golden/make_golden_big.py for the BASELINE.json configurations.
  *
- * usage: ref_driver [--dump FILE] [--summary FILE] [--time N] [--warmup W] [--both_sides 0|1] [--dlk N_EDGES] -- <phyml args>
+ *   --dump_pars FILE : parsimony (src/pars.c): after Pars(NULL) with both_sides == YES writes the Fitch sets
+ *                 and step counts of both sides of every edge (ui_l/ui_r, pars_l/pars_r), site_pars, c_pars,
+ *                 Pars(b) at every edge, and the same for the general (step-matrix) variant (p_pars_l/r)
+ *                 -- read by tests/golden/make_golden_pars.py.
+ *
+ * usage: ref_driver [--dump FILE] [--summary FILE] [--dump_pars FILE] [--time N] [--warmup W] [--both_sides 0|1]
+ *                   [--dlk N_EDGES] -- <phyml args>
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -209,6 +215,71 @@ static void dump_all(t_tree *tree, int n_dlk_edges)
   }
 }
 
+/* parsimony state of the reference: Pars (pars.c:20), Update_Partial_Pars (pars.c:239), Pars_Core (pars.c:397) */
+static void dump_pars(t_tree *tree)
+{
+  const int n_otu = tree->n_otu;
+  const int P = tree->data->n_pattern;
+  const int ns = tree->mod->ns;
+  const int n_edges = 2 * n_otu - 3;
+  const int init_general = tree->mod->s_opt->general_pars;
+  int *edge_pars = (int *)malloc(sizeof(int) * n_edges);
+  char nm[64];
+  int e, g;
+
+  rec_1i("n_otu", n_otu);
+  rec_1i("n_pattern", P);
+  rec_1i("ns", ns);
+  rec_i("step_mat", ns * ns, tree->step_mat);
+  rec_d("wght", P, tree->data->wght);
+  for (e = 0; e < n_edges; ++e)
+  {
+    int lr[2];
+    lr[0] = tree->a_edges[e]->left->num;
+    lr[1] = tree->a_edges[e]->rght->num;
+    sprintf(nm, "edge%d.nodes", e);
+    rec_i(nm, 2, lr);
+  }
+  Set_Both_Sides(YES, tree);
+  for (g = 0; g < 2; ++g)
+  {
+    const char *sfx = g ? "_general" : "";
+    tree->mod->s_opt->general_pars = g ? YES : NO;
+    Pars(NULL, tree);
+    sprintf(nm, "c_pars%s", sfx);
+    rec_1i(nm, tree->c_pars);
+    sprintf(nm, "site_pars%s", sfx);
+    rec_i(nm, P, tree->site_pars);
+    for (e = 0; e < n_edges; ++e)
+    {
+      t_edge *b = tree->a_edges[e];
+      if (!g)
+      {
+        sprintf(nm, "edge%d.ui_l", e);
+        rec_i(nm, P, b->ui_l);
+        sprintf(nm, "edge%d.ui_r", e);
+        rec_i(nm, P, b->ui_r);
+        sprintf(nm, "edge%d.pars_l", e);
+        rec_i(nm, P, b->pars_l);
+        sprintf(nm, "edge%d.pars_r", e);
+        rec_i(nm, P, b->pars_r);
+      }
+      else
+      {
+        sprintf(nm, "edge%d.p_pars_l", e);
+        rec_i(nm, (long long)P * ns, b->p_pars_l);
+        sprintf(nm, "edge%d.p_pars_r", e);
+        rec_i(nm, (long long)P * ns, b->p_pars_r);
+      }
+    }
+    for (e = 0; e < n_edges; ++e) edge_pars[e] = Pars(tree->a_edges[e], tree);
+    sprintf(nm, "edge_pars%s", sfx);
+    rec_i(nm, n_edges, edge_pars);
+  }
+  tree->mod->s_opt->general_pars = init_general;
+  free(edge_pars);
+}
+
 static void dump_summary(t_tree *tree)
 {
   const int P = tree->data->n_pattern;
@@ -239,7 +310,7 @@ static void dump_summary(t_tree *tree)
 
 int main(int argc, char **argv)
 {
-  const char *dump_file = NULL, *summary_file = NULL;
+  const char *dump_file = NULL, *summary_file = NULL, *pars_file = NULL;
   int n_time = 0, n_warm = 0, both_sides = 0, n_dlk = 4;
   int i, split = -1;
   option *io;
@@ -258,6 +329,8 @@ int main(int argc, char **argv)
       dump_file = argv[++i];
     else if (!strcmp(argv[i], "--summary") && i + 1 < argc)
       summary_file = argv[++i];
+    else if (!strcmp(argv[i], "--dump_pars") && i + 1 < argc)
+      pars_file = argv[++i];
     else if (!strcmp(argv[i], "--time") && i + 1 < argc)
       n_time = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--warmup") && i + 1 < argc)
@@ -346,6 +419,19 @@ int main(int argc, char **argv)
       return 1;
     }
     dump_summary(tree);
+    fclose(g_out);
+    g_out = NULL;
+  }
+
+  if (pars_file)
+  {
+    g_out = fopen(pars_file, "wb");
+    if (!g_out)
+    {
+      perror(pars_file);
+      return 1;
+    }
+    dump_pars(tree);
     fclose(g_out);
     g_out = NULL;
   }

@@ -12,6 +12,7 @@
 
 #include "../../include/phyml_b200.h"
 #include "plk_kernels.cuh"
+#include "plk_pars.cuh"
 
 using namespace plk;
 
@@ -147,6 +148,17 @@ struct plk_instance
   std::vector<plk_instance *> shards;
   std::vector<int>            shard_lo;
   bool                        inproc_p2p = false;
+
+  // parsimony (plk_pars_*, src/pars.c): one Fitch buffer int2{ui, pars}[P] per handle and, once a step matrix
+  // has been given, one state-major step-matrix buffer int[ns][pars_pstride] per handle; storage is lazy
+  int                 pars_n = 0;
+  std::vector<int2 *> pars_fitch;
+  std::vector<int *>  pars_sank;
+  size_t              pars_pstride = 0;
+  int                *d_step_mat = nullptr;
+  int                *d_site_pars = nullptr;
+  bool                pars_site_valid = false;
+  bool                wght_integral = true;  // every pattern weight is an integer (plk_set_pattern_weights)
 
   // scheduling scratch
   std::vector<int> lvl_write, lvl_read, op_level;
@@ -542,6 +554,10 @@ void plk_destroy(plk_instance *inst)
   cudaFree(inst->d_ticket);
   cudaFree(inst->d_result);
   cudaFree(inst->d_stage);
+  for (int2 *p : inst->pars_fitch) cudaFree(p);
+  for (int *p : inst->pars_sank) cudaFree(p);
+  cudaFree(inst->d_step_mat);
+  cudaFree(inst->d_site_pars);
   if (inst->h_result) cudaFreeHost(inst->h_result);
   for (int s = 0; s < kStageSlots; ++s)
   {
@@ -575,6 +591,9 @@ int plk_set_pattern_weights(plk_instance *inst, const double *wght, const short 
   }
   USE_DEVICE(inst);
   const size_t P = inst->cfg.n_patterns;
+  inst->wght_integral = true;
+  for (size_t s = 0; s < P; ++s)
+    if (!(wght[s] >= 0.0 && wght[s] < 9.0e15 && wght[s] == (double)(long long)wght[s])) inst->wght_integral = false;
   CU_TRY(inst, cudaMemcpyAsync(inst->d_wght, wght, P * sizeof(double), cudaMemcpyHostToDevice, inst->stream));
   if (invar)
     CU_TRY(inst, cudaMemcpyAsync(inst->d_invar, invar, P * sizeof(short), cudaMemcpyHostToDevice, inst->stream));
@@ -1990,5 +2009,345 @@ size_t plk_device_bytes(const plk_instance *inst)
 }
 void *plk_stream(plk_instance *inst) { return (void *)(inst->shards.empty() ? inst->stream : inst->shards[0]->stream); }
 int   plk_n_shards(const plk_instance *inst) { return inst->shards.empty() ? 1 : (int)inst->shards.size(); }
+
+}  // extern "C"
+
+// ---- parsimony (src/pars.c) -------------------------------------------------------------------------------
+namespace
+{
+int pars_check(plk_instance *inst, int h, bool general, bool need_data)
+{
+  ARG_CHECK(inst, inst->pars_n > 0, "parsimony buffers were not created (plk_pars_create)");
+  ARG_CHECK(inst, h >= 0 && h < inst->pars_n, "parsimony buffer handle out of range");
+  if (general) ARG_CHECK(inst, inst->d_step_mat != nullptr, "step-matrix parsimony needs the step matrix (plk_pars_create)");
+  if (need_data)
+    ARG_CHECK(inst, general ? inst->pars_sank[h] != nullptr : inst->pars_fitch[h] != nullptr,
+              "parsimony buffer read before it was ever written");
+  return PLK_OK;
+}
+
+int pars_ensure(plk_instance *inst, int h, bool general)
+{
+  if (general)
+  {
+    if (inst->pars_sank[h]) return PLK_OK;
+    const size_t n = inst->pars_pstride * inst->cfg.ns;
+    int          rc = dev_alloc(inst, &inst->pars_sank[h], n);
+    if (rc) return rc;
+    CU_TRY(inst, cudaMemsetAsync(inst->pars_sank[h], 0, n * sizeof(int), inst->stream));  // mCalloc, make.c:459
+    return PLK_OK;
+  }
+  if (inst->pars_fitch[h]) return PLK_OK;
+  int rc = dev_alloc(inst, &inst->pars_fitch[h], (size_t)inst->cfg.n_patterns);
+  if (rc) return rc;
+  CU_TRY(inst, cudaMemsetAsync(inst->pars_fitch[h], 0, (size_t)inst->cfg.n_patterns * sizeof(int2), inst->stream));
+  return PLK_OK;
+}
+
+void *pars_ptr(plk_instance *inst, int h, bool general)
+{
+  return general ? (void *)inst->pars_sank[h] : (void *)inst->pars_fitch[h];
+}
+
+// a result block that is published by the kernel itself, outside the cross-GPU exchange sequence
+ReduceOut make_publish_out(plk_instance *inst)
+{
+  ReduceOut ro;
+  ro.partials = inst->d_partials;
+  ro.ticket = inst->d_ticket;
+  ro.warn_flag = inst->d_warn;
+  ro.dev_out = inst->d_result;
+  ro.host_out = inst->h_result_dev;
+  ro.seq = ++inst->seq;
+  ro.coll_seq = 0;
+  ro.publish = 1;
+  ro.peers = nullptr;
+  ro.rank = 0;
+  ro.world = 1;
+  return ro;
+}
+
+// one launch (per 10 922 updates): the whole list, then (edge_mode != 0) the site loop of Pars at (left, rght)
+int pars_launch(plk_instance *inst, bool general, int n_ops, const plk_pars_op *ops, int edge_mode, int left, int rght)
+{
+  USE_DEVICE(inst);
+  int rc;
+  for (int i = 0; i < n_ops; ++i)
+  {
+    // sources first: an update may read the buffer it overwrites only if that buffer already holds data
+    if ((rc = pars_check(inst, ops[i].c1, general, true))) return rc;
+    if ((rc = pars_check(inst, ops[i].c2, general, true))) return rc;
+    if ((rc = pars_check(inst, ops[i].dst, general, false))) return rc;
+    if ((rc = pars_ensure(inst, ops[i].dst, general))) return rc;
+  }
+  ParsEdgeDev edge;
+  memset(&edge, 0, sizeof(edge));
+  if (edge_mode)
+  {
+    if ((rc = pars_check(inst, left, general, true))) return rc;
+    if ((rc = pars_check(inst, rght, general, true))) return rc;
+    edge.left = pars_ptr(inst, left, general);
+    edge.rght = pars_ptr(inst, rght, general);
+    edge.wght = inst->d_wght;
+    edge.site_pars = inst->d_site_pars;
+  }
+  const int P = inst->cfg.n_patterns;
+  const int per_slot = (int)(kStageBytes / sizeof(ParsOpDev));
+  int       done = 0;
+  std::vector<ParsOpDev> dev;
+  do
+  {
+    const int n = std::min(per_slot, n_ops - done);
+    const bool last = (done + n == n_ops);
+    dev.resize((size_t)std::max(n, 1));
+    for (int i = 0; i < n; ++i)
+    {
+      dev[i].dst = pars_ptr(inst, ops[done + i].dst, general);
+      dev[i].c1 = pars_ptr(inst, ops[done + i].c1, general);
+      dev[i].c2 = pars_ptr(inst, ops[done + i].c2, general);
+    }
+    void *d_ops = nullptr;
+    if (n > 0 && (rc = stage_upload(inst, dev.data(), sizeof(ParsOpDev) * (size_t)n, &d_ops))) return rc;
+    ParsEdgeDev e = edge;
+    e.mode = last ? edge_mode : 0;
+    if (e.mode == 1) e.ro = make_reduce_out(inst);
+    if (general)
+    {
+      const int grid = std::max(1, std::min((P + 127) / 128, kMaxReduceBlocks));
+      const int ns = inst->cfg.ns;
+      if (ns == 4)
+        k_pars_sankoff<4><<<grid, 128, 0, inst->stream>>>((const ParsOpDev *)d_ops, n, P, inst->pars_pstride, ns,
+                                                          inst->d_step_mat, e);
+      else if (ns == 20)
+        k_pars_sankoff<20><<<grid, 128, 0, inst->stream>>>((const ParsOpDev *)d_ops, n, P, inst->pars_pstride, ns,
+                                                           inst->d_step_mat, e);
+      else
+        k_pars_sankoff<0><<<grid, 128, 0, inst->stream>>>((const ParsOpDev *)d_ops, n, P, inst->pars_pstride, ns,
+                                                          inst->d_step_mat, e);
+    }
+    else
+    {
+      // patterns per thread: 1 while one pattern per thread still fits 8 blocks per SM, more only for very long
+      // alignments (the per-block partial sums of the epilogue bound the grid at kMaxReduceBlocks)
+      const long long t1 = (long long)kParsThreads * inst->num_sms * 8;
+      int             U = (P <= t1) ? 1 : (P <= 2 * t1) ? 2 : 4;
+      while ((long long)U * kParsThreads * kMaxReduceBlocks < P && U < 8) U *= 2;
+      ARG_CHECK(inst, (long long)U * kParsThreads * kMaxReduceBlocks >= P, "parsimony: too many patterns for one instance");
+      const int grid = std::max(1, (int)(((long long)P + (long long)U * kParsThreads - 1) / ((long long)U * kParsThreads)));
+      if (U == 1)
+        k_pars_fitch<1><<<grid, kParsThreads, 0, inst->stream>>>((const ParsOpDev *)d_ops, n, P, e);
+      else if (U == 2)
+        k_pars_fitch<2><<<grid, kParsThreads, 0, inst->stream>>>((const ParsOpDev *)d_ops, n, P, e);
+      else if (U == 4)
+        k_pars_fitch<4><<<grid, kParsThreads, 0, inst->stream>>>((const ParsOpDev *)d_ops, n, P, e);
+      else
+        k_pars_fitch<8><<<grid, kParsThreads, 0, inst->stream>>>((const ParsOpDev *)d_ops, n, P, e);
+    }
+    inst->launches++;
+    CU_TRY(inst, cudaGetLastError());
+    done += n;
+  } while (done < n_ops);
+  if (edge_mode) inst->pars_site_valid = true;
+  return PLK_OK;
+}
+
+// the weighted total of the site_pars just written, accumulated like the reference's int (pars.c:46)
+int pars_chain(plk_instance *inst, int carry_in, int *carry_out)
+{
+  USE_DEVICE(inst);
+  k_pars_chain<<<1, 32, 0, inst->stream>>>(inst->d_site_pars, inst->d_wght, inst->cfg.n_patterns, carry_in,
+                                           make_publish_out(inst));
+  inst->launches++;
+  CU_TRY(inst, cudaGetLastError());
+  double v = 0.0;
+  const int rc = finish_reduction(inst, &v, nullptr, nullptr);
+  if (rc) return rc;
+  *carry_out = (int)v;
+  return PLK_OK;
+}
+
+bool pars_all_integral(const plk_instance *inst)
+{
+  if (inst->shards.empty()) return inst->wght_integral;
+  for (const plk_instance *sh : inst->shards)
+    if (!sh->wght_integral) return false;
+  return true;
+}
+}  // namespace
+
+extern "C" {
+
+int plk_pars_create(plk_instance *inst, int n_buffers, const int *step_mat)
+{
+  ARG_CHECK(inst, n_buffers > 0, "plk_pars_create: n_buffers must be positive");
+  if (!inst->shards.empty())
+  {
+    FOR_SHARDS(inst, plk_pars_create(sh, n_buffers, step_mat));
+    inst->pars_n = n_buffers;
+    return PLK_OK;
+  }
+  USE_DEVICE(inst);
+  ARG_CHECK(inst, inst->pars_n == 0, "plk_pars_create: already created");
+  const int ns = inst->cfg.ns;
+  inst->pars_n = n_buffers;
+  inst->pars_fitch.assign((size_t)n_buffers, nullptr);
+  inst->pars_sank.assign((size_t)n_buffers, nullptr);
+  inst->pars_pstride = ((size_t)inst->cfg.n_patterns + 31) & ~(size_t)31;
+  int rc = dev_alloc(inst, &inst->d_site_pars, (size_t)inst->cfg.n_patterns);
+  if (rc) return rc;
+  if (step_mat)
+  {
+    if ((rc = dev_alloc(inst, &inst->d_step_mat, (size_t)ns * ns))) return rc;
+    CU_TRY(inst, cudaMemcpyAsync(inst->d_step_mat, step_mat, sizeof(int) * ns * ns, cudaMemcpyHostToDevice, inst->stream));
+    CU_TRY(inst, cudaStreamSynchronize(inst->stream));
+  }
+  return PLK_OK;
+}
+
+int plk_pars_set_buffer(plk_instance *inst, int buf, const int *ui, const int *pars, const int *p_pars)
+{
+  ARG_CHECK(inst, (ui && pars) || p_pars, "plk_pars_set_buffer: nothing to upload");
+  ARG_CHECK(inst, (ui == nullptr) == (pars == nullptr), "plk_pars_set_buffer: ui and pars go together");
+  if (!inst->shards.empty())
+  {
+    const int ns = inst->shards[0]->cfg.ns;
+    FOR_SHARDS(inst, plk_pars_set_buffer(sh, buf, ui ? ui + lo : nullptr, pars ? pars + lo : nullptr,
+                                         p_pars ? p_pars + lo * ns : nullptr));
+    return PLK_OK;
+  }
+  USE_DEVICE(inst);
+  const size_t P = (size_t)inst->cfg.n_patterns;
+  int          rc;
+  if (ui)
+  {
+    if ((rc = pars_check(inst, buf, false, false)) || (rc = pars_ensure(inst, buf, false))) return rc;
+    std::vector<int2> tmp(P);
+    for (size_t s = 0; s < P; ++s) tmp[s] = make_int2(ui[s], pars[s]);
+    CU_TRY(inst, cudaMemcpyAsync(inst->pars_fitch[buf], tmp.data(), P * sizeof(int2), cudaMemcpyHostToDevice, inst->stream));
+    CU_TRY(inst, cudaStreamSynchronize(inst->stream));
+  }
+  if (p_pars)
+  {
+    if ((rc = pars_check(inst, buf, true, false)) || (rc = pars_ensure(inst, buf, true))) return rc;
+    const int        ns = inst->cfg.ns;
+    std::vector<int> tmp(inst->pars_pstride * ns, 0);
+    for (size_t s = 0; s < P; ++s)
+      for (int j = 0; j < ns; ++j) tmp[(size_t)j * inst->pars_pstride + s] = p_pars[s * ns + j];
+    CU_TRY(inst, cudaMemcpyAsync(inst->pars_sank[buf], tmp.data(), tmp.size() * sizeof(int), cudaMemcpyHostToDevice, inst->stream));
+    CU_TRY(inst, cudaStreamSynchronize(inst->stream));
+  }
+  return PLK_OK;
+}
+
+int plk_pars_get_buffer(plk_instance *inst, int buf, int *ui, int *pars, int *p_pars)
+{
+  if (!inst->shards.empty())
+  {
+    const int ns = inst->shards[0]->cfg.ns;
+    FOR_SHARDS(inst, plk_pars_get_buffer(sh, buf, ui ? ui + lo : nullptr, pars ? pars + lo : nullptr,
+                                         p_pars ? p_pars + lo * ns : nullptr));
+    return PLK_OK;
+  }
+  USE_DEVICE(inst);
+  const size_t P = (size_t)inst->cfg.n_patterns;
+  int          rc;
+  if (ui || pars)
+  {
+    if ((rc = pars_check(inst, buf, false, true))) return rc;
+    std::vector<int2> tmp(P);
+    CU_TRY(inst, cudaMemcpyAsync(tmp.data(), inst->pars_fitch[buf], P * sizeof(int2), cudaMemcpyDeviceToHost, inst->stream));
+    CU_TRY(inst, cudaStreamSynchronize(inst->stream));
+    for (size_t s = 0; s < P; ++s)
+    {
+      if (ui) ui[s] = tmp[s].x;
+      if (pars) pars[s] = tmp[s].y;
+    }
+  }
+  if (p_pars)
+  {
+    if ((rc = pars_check(inst, buf, true, true))) return rc;
+    const int        ns = inst->cfg.ns;
+    std::vector<int> tmp(inst->pars_pstride * ns);
+    CU_TRY(inst, cudaMemcpyAsync(tmp.data(), inst->pars_sank[buf], tmp.size() * sizeof(int), cudaMemcpyDeviceToHost, inst->stream));
+    CU_TRY(inst, cudaStreamSynchronize(inst->stream));
+    for (size_t s = 0; s < P; ++s)
+      for (int j = 0; j < ns; ++j) p_pars[s * ns + j] = tmp[(size_t)j * inst->pars_pstride + s];
+  }
+  return PLK_OK;
+}
+
+int plk_pars_update(plk_instance *inst, int general, int n_ops, const plk_pars_op *ops)
+{
+  ARG_CHECK(inst, n_ops >= 0 && (n_ops == 0 || ops), "plk_pars_update: bad arguments");
+  if (n_ops == 0) return PLK_OK;
+  if (!inst->shards.empty())
+  {
+    FOR_SHARDS(inst, pars_launch(sh, general != 0, n_ops, ops, 0, -1, -1));
+    return PLK_OK;
+  }
+  return pars_launch(inst, general != 0, n_ops, ops, 0, -1, -1);
+}
+
+int plk_pars_traverse_edge(plk_instance *inst, int general, int n_ops, const plk_pars_op *ops, int left, int rght,
+                           int *c_pars)
+{
+  ARG_CHECK(inst, c_pars != nullptr && n_ops >= 0 && (n_ops == 0 || ops), "plk_pars_traverse_edge: bad arguments");
+  const bool integral = pars_all_integral(inst);
+  const int  mode = integral ? 1 : 2;
+  double     v = 0.0;
+  int        rc;
+  if (!inst->shards.empty())
+  {
+    FOR_SHARDS(inst, pars_launch(sh, general != 0, n_ops, ops, mode, left, rght));
+    if (integral)
+    {
+      if ((rc = finish_sharded(inst, &v, nullptr, nullptr))) return rc;
+      *c_pars = (int)v;
+      return PLK_OK;
+    }
+    int c = 0;
+    FOR_SHARDS(inst, pars_chain(sh, c, &c));  // pattern order = shard order
+    *c_pars = c;
+    return PLK_OK;
+  }
+  if ((rc = pars_launch(inst, general != 0, n_ops, ops, mode, left, rght))) return rc;
+  if (integral)
+  {
+    if ((rc = finish_reduction(inst, &v, nullptr, nullptr))) return rc;
+    *c_pars = (int)v;
+    return PLK_OK;
+  }
+  if (inst->world > 1 || inst->allreduce)
+  {
+    inst->err = "parsimony with non-integral pattern weights is not supported across processes";
+    return PLK_ERR_UNSUPPORTED;
+  }
+  return pars_chain(inst, 0, c_pars);
+}
+
+int plk_pars_edge(plk_instance *inst, int general, int left, int rght, int *c_pars)
+{
+  return plk_pars_traverse_edge(inst, general, 0, nullptr, left, rght, c_pars);
+}
+
+int plk_get_site_pars(plk_instance *inst, int *site_pars)
+{
+  ARG_CHECK(inst, site_pars != nullptr, "plk_get_site_pars: NULL output");
+  if (!inst->shards.empty())
+  {
+    FOR_SHARDS(inst, plk_get_site_pars(sh, site_pars + lo));
+    return PLK_OK;
+  }
+  USE_DEVICE(inst);
+  if (!inst->pars_site_valid)
+  {
+    inst->err = "plk_get_site_pars: no parsimony score has been computed yet";
+    return PLK_ERR_STATE;
+  }
+  CU_TRY(inst, cudaMemcpyAsync(site_pars, inst->d_site_pars, (size_t)inst->cfg.n_patterns * sizeof(int),
+                               cudaMemcpyDeviceToHost, inst->stream));
+  CU_TRY(inst, cudaStreamSynchronize(inst->stream));
+  return PLK_OK;
+}
 
 }  // extern "C"

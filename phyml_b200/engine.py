@@ -47,6 +47,8 @@ EXPORTS = [
     "plk_get_dot_prod", "plk_comm_unique_id", "plk_comm_init", "plk_comm_set_allreduce",
     "plk_comm_p2p_export", "plk_comm_p2p_init", "plk_create_sharded", "plk_n_shards",
     "plk_launch_count", "plk_device_bytes", "plk_stream", "plk_version",
+    "plk_pars_create", "plk_pars_set_buffer", "plk_pars_get_buffer", "plk_pars_update", "plk_pars_edge",
+    "plk_pars_traverse_edge", "plk_get_site_pars",
 ]
 
 _lib = None
@@ -104,6 +106,13 @@ def load_library() -> C.CDLL:
     lib.plk_stream.argtypes = [vp]
     lib.plk_stream.restype = vp
     lib.plk_version.restype = C.c_char_p
+    lib.plk_pars_create.argtypes = [vp, C.c_int, vp]
+    lib.plk_pars_set_buffer.argtypes = [vp, C.c_int, vp, vp, vp]
+    lib.plk_pars_get_buffer.argtypes = [vp, C.c_int, vp, vp, vp]
+    lib.plk_pars_update.argtypes = [vp, C.c_int, C.c_int, vp]
+    lib.plk_pars_edge.argtypes = [vp, C.c_int, C.c_int, C.c_int, ip]
+    lib.plk_pars_traverse_edge.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, ip]
+    lib.plk_get_site_pars.argtypes = [vp, vp]
     _lib = lib
     return lib
 
@@ -348,6 +357,50 @@ class Engine:
     def get_dot_prod(self) -> np.ndarray:
         out = np.empty((self.P, self.ncatg, self.ns))
         self._ck(self.lib.plk_get_dot_prod(self.h, _ptr(out)))
+        return out
+
+    # ------------------------------------------------------------------ parsimony (src/pars.c)
+    def pars_create(self, n_buffers: int, step_mat=None):
+        sm = None if step_mat is None else np.ascontiguousarray(step_mat, dtype=np.int32).reshape(self.ns, self.ns)
+        self._ck(self.lib.plk_pars_create(self.h, n_buffers, None if sm is None else _ptr(sm)))
+
+    def pars_set_buffer(self, buf: int, ui=None, pars=None, p_pars=None):
+        a = [None if x is None else np.ascontiguousarray(x, dtype=np.int32) for x in (ui, pars, p_pars)]
+        assert all(x is None or x.size == n for x, n in zip(a, (self.P, self.P, self.P * self.ns)))
+        self._ck(self.lib.plk_pars_set_buffer(self.h, buf, *[None if x is None else _ptr(x) for x in a]))
+
+    def pars_get_buffer(self, buf: int, general: bool = False):
+        if general:
+            pp = np.empty((self.P, self.ns), dtype=np.int32)
+            self._ck(self.lib.plk_pars_get_buffer(self.h, buf, None, None, _ptr(pp)))
+            return pp
+        ui, pars = np.empty(self.P, dtype=np.int32), np.empty(self.P, dtype=np.int32)
+        self._ck(self.lib.plk_pars_get_buffer(self.h, buf, _ptr(ui), _ptr(pars), None))
+        return ui, pars
+
+    @staticmethod
+    def _pars_ops(ops) -> np.ndarray:
+        return np.ascontiguousarray(np.asarray(ops, dtype=np.int32).reshape(-1, 3))
+
+    def pars_update(self, ops, general: bool = False):
+        arr = self._pars_ops(ops)
+        self._ck(self.lib.plk_pars_update(self.h, int(general), len(arr), _ptr(arr)))
+
+    def pars_edge(self, left: int, rght: int, general: bool = False) -> int:
+        out = C.c_int(0)
+        self._ck(self.lib.plk_pars_edge(self.h, int(general), left, rght, C.byref(out)))
+        return out.value
+
+    def pars_traverse_edge(self, ops, left: int, rght: int, general: bool = False) -> int:
+        arr = self._pars_ops(ops)
+        out = C.c_int(0)
+        self._ck(self.lib.plk_pars_traverse_edge(self.h, int(general), len(arr), _ptr(arr) if len(arr) else None,
+                                                 left, rght, C.byref(out)))
+        return out.value
+
+    def get_site_pars(self) -> np.ndarray:
+        out = np.empty(self.P, dtype=np.int32)
+        self._ck(self.lib.plk_get_site_pars(self.h, _ptr(out)))
         return out
 
     # ------------------------------------------------------------------ site sharding

@@ -168,6 +168,18 @@ class Tree:
             ops += self.pre_order_ops()
         return ops
 
+    # ------------------------------------------------------------------ Update_Partial_Pars
+    def pars_ops(self, ops: Sequence[PartialOp]) -> List[Tuple[int, int, int]]:
+        """The same traversal as parsimony updates (Update_Partial_Pars, src/pars.c:239-351): every edge side,
+        tips included, owns a parsimony buffer; handle = 2*edge + side (a tip is always on the right)."""
+        def h(c: Side, e: int) -> int:
+            return c.clv if not c.is_tip else 2 * e + RGHT
+        return [(o.dst, h(o.c1, o.pmat1), h(o.c2, o.pmat2)) for o in ops]
+
+    def pars_tip_handle(self, tip: int) -> int:
+        """Buffer of a tip: ui_r / p_pars_r of its only edge (Init_Ui_Tips, src/pars.c:164-233)."""
+        return 2 * self.adj[tip][0][0] + RGHT
+
     @property
     def root_edge(self) -> int:
         """Edge at which Lk(NULL) sums site likelihoods: a_nodes[tip_root]->b[0] (src/lk.c:578-579)."""

@@ -198,6 +198,49 @@ class OracleBackend:
     def get_dot_prod(self):
         return self.dot_prod.copy()
 
+    # ---- parsimony (oracle restatement of src/pars.c)
+    def pars_create(self, n_buffers, step_mat=None):
+        self.step_mat = None if step_mat is None else np.ascontiguousarray(step_mat, dtype=np.int32)
+        self.p_ui, self.p_pars, self.p_pp = {}, {}, {}
+        self.site_pars = np.zeros(self.P, dtype=np.int32)
+
+    def pars_set_buffer(self, buf, ui=None, pars=None, p_pars=None):
+        if ui is not None:
+            self.p_ui[buf] = np.ascontiguousarray(ui, dtype=np.int32).copy()
+            self.p_pars[buf] = np.ascontiguousarray(pars, dtype=np.int32).copy()
+        if p_pars is not None:
+            self.p_pp[buf] = np.ascontiguousarray(p_pars, dtype=np.int32).reshape(self.P, self.ns).copy()
+
+    def pars_get_buffer(self, buf, general=False):
+        return self.p_pp[buf].copy() if general else (self.p_ui[buf].copy(), self.p_pars[buf].copy())
+
+    def pars_update(self, ops, general=False):
+        for dst, c1, c2 in np.asarray(ops, dtype=np.int64).reshape(-1, 3).tolist():
+            if general:
+                out = np.zeros((self.P, self.ns), dtype=np.int32)
+                self.lib.plk_oracle_pars_update_general(self.ns, self.P, _p(self.step_mat), _p(out),
+                                                        _p(self.p_pp[c1]), _p(self.p_pp[c2]))
+                self.p_pp[dst] = out
+            else:
+                ui, pars = np.zeros(self.P, dtype=np.int32), np.zeros(self.P, dtype=np.int32)
+                self.lib.plk_oracle_pars_update(self.P, _p(ui), _p(pars), _p(self.p_ui[c1]), _p(self.p_pars[c1]),
+                                                _p(self.p_ui[c2]), _p(self.p_pars[c2]))
+                self.p_ui[dst], self.p_pars[dst] = ui, pars
+
+    def pars_edge(self, left, rght, general=False):
+        g = lambda d, k: _p(d[k]) if k in d else None
+        return int(self.lib.plk_oracle_pars_edge(int(general), self.ns, self.P, _dp(self.wght), _p(self.step_mat),
+                                                 g(self.p_ui, left), g(self.p_pars, left), g(self.p_pp, left),
+                                                 g(self.p_ui, rght), g(self.p_pars, rght), g(self.p_pp, rght),
+                                                 _p(self.site_pars)))
+
+    def pars_traverse_edge(self, ops, left, rght, general=False):
+        self.pars_update(ops, general)
+        return self.pars_edge(left, rght, general)
+
+    def get_site_pars(self):
+        return self.site_pars.copy()
+
     def sync(self):
         pass
 

@@ -73,8 +73,38 @@ def test_spr_search(tmp_path):
     args = ["-i", "small.phy", "-d", "nt", "-m", "HKY85", "-c", "4", "-a", "0.5", "-f", "e", "-o", "tlr", "-s", "SPR",
             "-b", "0", "--r_seed", "1", "--no_memory_check"]
     a, out = run(B200, str(tmp_path), args, {"PLK_SHIM_VERBOSE": "1"})
+    topo_a = _topology(str(tmp_path), "small.phy")
+    b, _ = run(REF, str(tmp_path), args)
+    topo_b = _topology(str(tmp_path), "small.phy")
+    assert abs(a - b) <= 1e-5 * abs(b), (a, b)
+    assert topo_a == topo_b
+    # the parsimony pre-filter of the search (spr_pars, init.c:786; pars.c) ran on the device as well
+    m = re.search(r"phyml_b200: Pars (\d+)  Update_Partial_Pars (\d+)", out)
+    assert m and int(m.group(1)) > 0 and int(m.group(2)) > 0, out[-1500:]
+
+
+@needs_bins
+def test_spr_search_step_matrix_parsimony(tmp_path):
+    """--g_pars: the step-matrix (Sankoff) branch of pars.c:355-372,409-431 as the pre-filter of the same search."""
+    phy, nwk = stage(tmp_path, "synth_dna_deep")
+    lines = open(os.path.join(str(tmp_path), phy)).read().splitlines()
+    n_sites = lines[0].split()[1]
+    with open(os.path.join(str(tmp_path), "small.phy"), "w") as f:
+        f.write(f"14 {n_sites}\n" + "\n".join(lines[1:15]) + "\n")
+    args = ["-i", "small.phy", "-d", "nt", "-m", "HKY85", "-c", "4", "-a", "0.5", "-f", "e", "-o", "tlr", "-s", "SPR",
+            "-b", "0", "--r_seed", "1", "--no_memory_check", "--g_pars"]
+    a, out = run(B200, str(tmp_path), args, {"PLK_SHIM_VERBOSE": "1"})
+    topo_a = _topology(str(tmp_path), "small.phy")
     b, _ = run(REF, str(tmp_path), args)
     assert abs(a - b) <= 1e-5 * abs(b), (a, b)
+    assert topo_a == _topology(str(tmp_path), "small.phy")
+    assert re.search(r"phyml_b200: Pars (\d+)", out)
+
+
+def _topology(tmp, phy):
+    """Newick of the tree PhyML wrote next to the alignment with branch lengths and supports removed."""
+    txt = open(os.path.join(tmp, phy + "_phyml_tree.txt")).read().strip()
+    return re.sub(r"\)[0-9.eE+-]+", ")", re.sub(r":[0-9.eE+-]+", "", txt))
 
 
 def _supports(tmp, phy):
