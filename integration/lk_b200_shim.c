@@ -26,8 +26,11 @@
  * src/utilities.c:6247-6430), so device buffers are keyed by the host pointer value
  * (p_lk_left / p_lk_rght / Pij_rr), never by edge number.  Tips are keyed by node number.
  *
+ * Rooted trees (n_root, Add_Root src/utilities.c:8426): the operands of every update are resolved by the
+ * reference's own Set_All_Partial_Lk (src/lk.c:2988-3194 are its rooted cases) and the two root edges
+ * (a_edges[2n-3], [2n-2]) own P-matrix / CLV handles like any other edge; Lk() follows lk.c:504-576.
  * Unsupported configurations abort like the BEAGLE hooks did (src/main.c:240-253): mixture trees
- * (is_mixt_tree), rooted trees (n_root), SCALE_RATE_SPECIFIC, M4, gamma_mgf_bl, ns > 32, and any
+ * (is_mixt_tree), SCALE_RATE_SPECIFIC, M4, gamma_mgf_bl, ns > 32, and any
  * likelihood call on a tree that has no device instance (bootstrap replicates share the main tree's
  * structures, src/utilities.c:4042) -- there is no silent CPU fallback.
  * Host-side readers of engine state: c_lnL_sorted / cur_site_lk / unscaled_site_lk_cat /
@@ -296,11 +299,11 @@ static void flush(shim_t *sh)
 
 static void check_supported(t_tree *tree)
 {
-  if (tree->is_mixt_tree == YES || tree->mixt_tree != NULL || tree->n_root != NULL || tree->mod->use_m4mod == YES ||
+  if (tree->is_mixt_tree == YES || tree->mixt_tree != NULL || tree->mod->use_m4mod == YES ||
       tree->mod->gamma_mgf_bl == YES || tree->scaling_method != SCALE_FAST || tree->mod->ns > 32 ||
       (tree->io && tree->io->do_alias_subpatt == YES))
   {
-    PhyML_Fprintf(stderr, "\n. phyml_b200: unsupported configuration (mixture / rooted tree / M4 / MGF branch lengths /"
+    PhyML_Fprintf(stderr, "\n. phyml_b200: unsupported configuration (mixture / M4 / MGF branch lengths /"
                           "\n. rate-specific scaling / sub-pattern aliasing): use the CPU build.\n");
     Exit("\n");
   }
@@ -498,6 +501,12 @@ void Update_Partial_Lk(t_tree *tree, t_edge *b, t_node *d)
   if (d->tax) return;
   Set_All_Partial_Lk(&n_v1, &n_v2, &p_lk, &sum_scale, &p_lk_loc, &Pij1, &tPij1, &p_lk_v1, &sum_scale_v1, &Pij2,
                      &tPij2, &p_lk_v2, &sum_scale_v2, d, b, tree);
+  if (!n_v1 || !n_v2)
+  { /* d == n_root with ignore_root == NO (lk.c:3010-3050): a one-child update.  The reference's own AVX / SSE /
+       default kernels dereference n_v1 there (avx.c:450, lk.c:1736), only its generic kernel survives it */
+    PhyML_Fprintf(stderr, "\n. phyml_b200: one-child update at the root node (ignore_root == NO) is not supported.\n");
+    Exit("\n");
+  }
   if (sh->n_queue == sh->queue_cap) flush(sh);
   op = &sh->queue[sh->n_queue++];
   op->dst = clv_handle(sh, p_lk);
@@ -559,15 +568,16 @@ phydbl Lk(t_edge *b, t_tree *tree)
   /* skip_tree_traversal (Optimiz_Alpha_And_Pinv, optimiz.c:2215-2222) only saves work in the
      reference; recomputing gives the same value, so it is ignored here */
   if (!b)
-  { /* lk.c:500-505: all P-matrices in one batched launch */
+  { /* lk.c:500-511: all P-matrices in one batched launch (+ the two root edges of a rooted tree) */
     flush(sh);
-    const int n = 2 * tree->n_otu - 3;
+    const int rooted = (tree->n_root != NULL && tree->ignore_root == NO);
+    const int n = 2 * tree->n_otu - 3 + (rooted ? 2 : 0);
     int      *h = (int *)malloc(sizeof(int) * n);
     double   *l = (double *)malloc(sizeof(double) * n);
     int       n_batched = 0;
     for (br = 0; br < (unsigned int)n; ++br)
     {
-      t_edge *e = tree->a_edges[br];
+      t_edge *e = (br < (unsigned int)(2 * tree->n_otu - 3)) ? tree->a_edges[br] : tree->n_root->b[br - (2 * tree->n_otu - 3) + 1];
       if (e->has_zero_br_len == YES)
         Update_PMat_At_Given_Edge(e, tree);
       else
@@ -581,11 +591,44 @@ phydbl Lk(t_edge *b, t_tree *tree)
     sh->n_pmat += n_batched;
     free(h);
     free(l);
-    /* lk.c:560-565: the reference's own recursion; every visit lands in Update_Partial_Lk above */
-    Post_Order_Lk(tree->a_nodes[tree->tip_root], tree->a_nodes[tree->tip_root]->v[0], tree);
-    if (tree->both_sides == YES) Pre_Order_Lk(tree->a_nodes[tree->tip_root], tree->a_nodes[tree->tip_root]->v[0], tree);
-    b = tree->a_nodes[tree->tip_root]->b[0]; /* lk.c:578-579 */
+    /* lk.c:529-566: the reference's own recursions; every visit lands in Update_Partial_Lk above */
+    if (tree->n_root != NULL)
+    {
+      if (tree->ignore_root == NO)
+      { /* rooted evaluation (PhyTime / PhyREX trees): both subtrees of the root, then the root's two edges */
+        Post_Order_Lk(tree->n_root, tree->n_root->v[1], tree);
+        Post_Order_Lk(tree->n_root, tree->n_root->v[2], tree);
+        Update_Partial_Lk(tree, tree->n_root->b[1], tree->n_root);
+        Update_Partial_Lk(tree, tree->n_root->b[2], tree->n_root);
+        if (tree->both_sides == YES)
+        {
+          Pre_Order_Lk(tree->n_root, tree->n_root->v[2], tree);
+          Pre_Order_Lk(tree->n_root, tree->n_root->v[1], tree);
+        }
+        b = (tree->n_root->v[1]->tax == NO) ? (tree->n_root->b[2]) : (tree->n_root->b[1]); /* lk.c:572-573 */
+      }
+      else
+      { /* the root is ignored: the traversal starts from both ends of the edge that carries it */
+        Post_Order_Lk(tree->e_root->rght, tree->e_root->left, tree);
+        Post_Order_Lk(tree->e_root->left, tree->e_root->rght, tree);
+        if (tree->both_sides == YES)
+        {
+          Pre_Order_Lk(tree->e_root->rght, tree->e_root->left, tree);
+          Pre_Order_Lk(tree->e_root->left, tree->e_root->rght, tree);
+        }
+        b = tree->e_root; /* lk.c:575 */
+      }
+    }
+    else
+    {
+      Post_Order_Lk(tree->a_nodes[tree->tip_root], tree->a_nodes[tree->tip_root]->v[0], tree);
+      if (tree->both_sides == YES) Pre_Order_Lk(tree->a_nodes[tree->tip_root], tree->a_nodes[tree->tip_root]->v[0], tree);
+      b = tree->a_nodes[tree->tip_root]->b[0]; /* lk.c:578-579 */
+    }
   }
+  else if (tree->use_eigen_lr == NO && tree->n_root && (b == tree->n_root->b[1] || b == tree->n_root->b[2]) &&
+           tree->ignore_root == YES)
+    Update_PMat_At_Given_Edge(tree->e_root, tree); /* lk.c:517-522 */
   else if (tree->use_eigen_lr == NO)
     Update_PMat_At_Given_Edge(b, tree); /* lk.c:515-527 */
 

@@ -23,8 +23,13 @@
  *                 Pars(b) at every edge, and the same for the general (step-matrix) variant (p_pars_l/r)
  *                 -- read by tests/golden/make_golden_pars.py.
  *
- * usage: ref_driver [--dump FILE] [--summary FILE] [--dump_pars FILE] [--time N] [--warmup W] [--both_sides 0|1]
- *                   [--dlk N_EDGES] -- <phyml args>
+ *   --rooted E  : Add_Root on edge E (src/utilities.c:8426) after the set-up, then Lk(NULL) with both_sides == YES
+ *                 (the tree->n_root branches of src/lk.c:529-576 with ignore_root == YES, the default) and Lk(b)
+ *                 at every 5th edge; prints one REF_ROOTED JSON line.  Host arrays are not read, so this mode also
+ *                 runs when the driver is linked against the B200 binding (integration/_build/ref_driver_b200).
+ *
+ * usage: ref_driver [--dump FILE] [--summary FILE] [--dump_pars FILE] [--rooted E] [--time N] [--warmup W]
+ *                   [--both_sides 0|1] [--dlk N_EDGES] -- <phyml args>
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -311,7 +316,7 @@ static void dump_summary(t_tree *tree)
 int main(int argc, char **argv)
 {
   const char *dump_file = NULL, *summary_file = NULL, *pars_file = NULL;
-  int n_time = 0, n_warm = 0, both_sides = 0, n_dlk = 4;
+  int n_time = 0, n_warm = 0, both_sides = 0, n_dlk = 4, rooted_edge = -1;
   int i, split = -1;
   option *io;
   calign *cdata;
@@ -331,6 +336,8 @@ int main(int argc, char **argv)
       summary_file = argv[++i];
     else if (!strcmp(argv[i], "--dump_pars") && i + 1 < argc)
       pars_file = argv[++i];
+    else if (!strcmp(argv[i], "--rooted") && i + 1 < argc)
+      rooted_edge = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--time") && i + 1 < argc)
       n_time = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--warmup") && i + 1 < argc)
@@ -408,6 +415,24 @@ int main(int argc, char **argv)
            tree->n_otu, tree->data->n_pattern, tree->mod->ns, tree->mod->ras->n_catg, both_sides, n_time,
            tot / n_time, best, tree->c_lnL);
     free(t);
+  }
+
+  if (rooted_edge >= 0)
+  {
+    const int n_edges = 2 * tree->n_otu - 3;
+    const double unrooted = tree->c_lnL;
+    int e, first = 1;
+    Add_Root(tree->a_edges[rooted_edge % n_edges], tree);
+    Set_Both_Sides(YES, tree);
+    Lk(NULL, tree);
+    printf("\nREF_ROOTED {\"root_edge\": %d, \"ignore_root\": %d, \"lnL_unrooted\": %.17g, \"lnL\": %.17g, \"edge_lnl\": [",
+           tree->e_root->num, tree->ignore_root, unrooted, tree->c_lnL);
+    for (e = 0; e < n_edges; e += 5)
+    {
+      printf("%s%.17g", first ? "" : ", ", Lk(tree->a_edges[e], tree));
+      first = 0;
+    }
+    printf("]}\n");
   }
 
   if (summary_file)

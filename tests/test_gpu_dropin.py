@@ -101,6 +101,33 @@ def test_spr_search_step_matrix_parsimony(tmp_path):
     assert re.search(r"phyml_b200: Pars (\d+)", out)
 
 
+@needs_bins
+def test_rooted_tree(tmp_path):
+    """A rooted t_tree (Add_Root, utilities.c:8426; the n_root branches of lk.c:529-576 and the rooted cases of
+    Set_All_Partial_Lk, lk.c:2988-3194, with ignore_root == YES): oracle/ref_driver.c --rooted linked against the
+    binding vs the same driver on the reference's CPU code.  main() never evaluates a rooted tree, hence the driver."""
+    import json
+    drv_b200 = os.path.join(ROOT, "integration", "_build", "ref_driver_b200")
+    drv_ref = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    if not (os.path.exists(drv_b200) and os.path.exists(drv_ref)):
+        pytest.skip("drivers not built")
+    phy, nwk = stage(tmp_path, "synth_dna_deep")
+    args = ["--rooted", "7", "--", "-i", phy, "-u", nwk, "-d", "nt", "-m", "GTR", "-c", "4", "-a", "0.5", "-f", "e", "-o", "n",
+            "-b", "0", "--r_seed", "1", "--no_memory_check"]
+    out = []
+    for drv in (drv_b200, drv_ref):
+        res = subprocess.run([drv] + args, cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+        out.append(json.loads(re.search(r"REF_ROOTED (\{.*\})", res.stdout).group(1)))
+    a, b = out
+    assert a["root_edge"] == b["root_edge"] == 7 and b["ignore_root"] == 1
+    assert abs(a["lnL"] - b["lnL"]) <= 1e-11 * abs(b["lnL"]), (a["lnL"], b["lnL"])
+    assert abs(a["lnL"] - (-21640.146617685834)) <= 1e-9 * abs(b["lnL"])
+    assert len(a["edge_lnl"]) == len(b["edge_lnl"]) > 10
+    for x, y in zip(a["edge_lnl"], b["edge_lnl"]):
+        assert abs(x - y) <= 1e-11 * abs(y), (x, y)
+
+
 def _topology(tmp, phy):
     """Newick of the tree PhyML wrote next to the alignment with branch lengths and supports removed."""
     txt = open(os.path.join(tmp, phy + "_phyml_tree.txt")).read().strip()

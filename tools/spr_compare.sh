@@ -23,5 +23,5 @@ if [ "$ONLY" != "b200" ]; then $ROOT/oracle/_ref/phyml_ref -i a.phy $ARGS > a.lo
 t2=$(date +%s.%N)
 echo "config: $NT taxa x $NS sites GTR+G4, -o tlr -s SPR"
 echo "B200 : wall $(python -c "print(round($t1-$t0,2))") s  $(grep -E 'Log likelihood of the current' b.log | tail -1)  $(grep -E 'Time used' b.log | tail -1)"
-grep -E "phyml_b200: (Lk|wall-clock|.*instance for)" b.log | tail -3
+grep -E "phyml_b200: (Lk|Pars|wall-clock|.*instance for)" b.log | tail -4
 echo "CPU  : wall $(python -c "print(round($t2-$t1,2))") s  $(grep -E 'Log likelihood of the current' a.log | tail -1)  $(grep -E 'Time used' a.log | tail -1)"
