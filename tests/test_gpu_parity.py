@@ -70,6 +70,7 @@ def _synthetic(ns, n_taxa, n_sites, seed, ambiguity, ncatg=4, pinv=0.0, mean_bl=
         m = pmodel.gtr(alpha=0.5, ncatg=ncatg, pinv=pinv)
     else:
         m = pmodel.lg_from_fixture(alpha=0.5, ncatg=ncatg)
+        m.pinv, m.invar = pinv, pinv > 0.0
     codes = alignment.simulate(tree, m, n_sites, seed=seed + 1, ambiguity=ambiguity)
     pat = alignment.compress(codes, ns)
     return tree, m, pat
@@ -84,6 +85,11 @@ def _synthetic(ns, n_taxa, n_sites, seed, ambiguity, ncatg=4, pinv=0.0, mean_bl=
     (4, 16, 999, 6, 0.0, 0.05, 0.1),      # ncatg not a power of two -> generic kernel
     (20, 10, 700, 4, 0.0, 0.02, 0.1),
     (20, 30, 301, 2, 0.0, 0.0, 0.2),
+    (20, 320, 70, 4, 0.0, 0.02, 0.45),    # deep 20-state tree: the 2^256 rescaling branch of the DMMA kernel fires
+    (20, 14, 500, 4, 0.15, 0.02, 0.1),    # 20 states with invariable sites (Invariant_Lk)
+    (20, 9, 333, 1, 0.0, 0.02, 0.1),      # 20 states, ncatg = 1
+    (20, 9, 333, 3, 0.1, 0.02, 0.1),      # 20 states, ncatg = 3
+    (20, 9, 333, 8, 0.0, 0.02, 0.1),      # 20 states, ncatg = 8
 ])
 def test_engine_vs_oracle_synthetic(ns, n_taxa, n_sites, ncatg, pinv, amb, mean_bl):
     """CUDA vs oracle through the reference-named host interface (LkTree): lnL, every CLV, scalers,
@@ -115,6 +121,34 @@ def test_engine_vs_oracle_synthetic(ns, n_taxa, n_sites, ncatg, pinv, amb, mean_
         assert rg[0] == rc[0]
         assert abs(rg[1] - rc[1]) <= 1e-12 * abs(rc[1])
         assert abs(gpu.c_dlnL - cpu.c_dlnL) <= 1e-9 * max(1.0, abs(cpu.c_dlnL))
+
+
+@pytest.mark.parametrize("ns", [4, 20])
+def test_deep_tree_rescaling_fires(ns):
+    """the deep synthetic trees above are only a test of the rescaling branch if scalers are non-zero"""
+    tree, m, pat = _synthetic(ns, 320, 70, 3, 0.02, 4, 0.0, 0.45)
+    args = (tree.n_otu, pat.n_pattern, ns, 4, tree.n_clv_handles, tree.n_edges)
+    gpu = LkTree(tree, pat, m, Engine(*args))
+    gpu.Lk()
+    left, _ = tree.edge_sides(tree.root_edge)
+    assert gpu.eng.get_clv(left.clv)[1].max() >= 256
+
+
+@pytest.mark.parametrize("ns,ncatg", [(4, 4), (20, 4), (4, 3)])
+def test_no_scaling_flag(ns, ncatg):
+    """PLK_FLAG_NO_SCALING (tree->apply_lk_scaling == NO, lk.c:1563,2701-2706): no rescaling, all scalers zero"""
+    tree, m, pat = _synthetic(ns, 24, 300, 7, 0.02, ncatg, 0.0, 0.1)
+    args = (tree.n_otu, pat.n_pattern, ns, ncatg, tree.n_clv_handles, tree.n_edges)
+    gpu = LkTree(tree, pat, m, Engine(*args, apply_scaling=False))
+    cpu = LkTree(tree, pat, m, OracleBackend(*args))
+    cpu.eng.apply_scaling = 0
+    lg, lc = gpu.Lk(), cpu.Lk()
+    assert abs(lg - lc) <= 1e-12 * abs(lc)
+    left, _ = tree.edge_sides(tree.root_edge)
+    a, sa = gpu.eng.get_clv(left.clv)
+    b, sb = cpu.eng.get_clv(left.clv)
+    assert (sa == 0).all() and (sb == 0).all()
+    np.testing.assert_allclose(a, b, rtol=1e-9, atol=0)
 
 
 def test_zero_weight_patterns_and_single_pattern():

@@ -1,9 +1,13 @@
 import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-import bench
+from phyml_b200 import workloads as wl
 from phyml_b200.engine import Engine, pack_ops
-tree, m, pat, codes, desc = bench.make_workload("dna_100x100k", 0, 1)
+name = "dna_100x100k"
+w = wl.WORKLOADS[name]
+m, _pin = wl.evaluation_model(name)
+tree = wl.make_tree(w)
+pat = wl.make_patterns(name, [0], procs=8)
 eng = Engine(tree.n_otu, pat.n_pattern, 4, 4, tree.n_clv_handles, tree.n_edges)
 eng.set_weights(pat.wght, pat.invar); eng.set_tip_table(pat.table()); eng.set_all_tip_codes(pat.codes); eng.set_model(m)
 ops = pack_ops(tree.post_order_ops()); edges = np.arange(tree.n_edges, dtype=np.int32); L = tree.l.copy()

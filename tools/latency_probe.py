@@ -9,12 +9,16 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 
-import bench
+from phyml_b200 import workloads as wl
 from phyml_b200.engine import Engine, pack_ops
 from phyml_b200.lk import LkTree
 
-wl = sys.argv[1] if len(sys.argv) > 1 else "dna_100x50k"
-tree, m, pat, codes, desc = bench.make_workload(wl, 0, 1)
+name = sys.argv[1] if len(sys.argv) > 1 else "dna_100x50k"
+w = wl.WORKLOADS[name]
+m, _pin = wl.evaluation_model(name)
+tree = wl.make_tree(w)
+pat = wl.make_patterns(name, wl.rank_blocks(w, 0, 1) if w.n_blocks > 1 else [0], procs=8)
+desc = w.desc
 eng = Engine(tree.n_otu, pat.n_pattern, m.ns, m.ncatg, tree.n_clv_handles, tree.n_edges)
 t = LkTree(tree, pat, m, eng)
 t.Set_Both_Sides(1)
