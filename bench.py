@@ -39,7 +39,6 @@ from phyml_b200 import alignment, workloads as wl  # noqa: E402
 METRIC = "site_edge_updates_per_s"
 UNIT = "site*edge-updates/s"
 PARITY_RTOL = 1e-9   # BASELINE.json north_star
-E2E_SHARDS_DEFAULT = 1   # pattern blocks of the e2e leg's instance on one GPU (copy/compute overlap), see measure()
 
 
 def default_workload(gpus):
@@ -241,45 +240,22 @@ def measure(name, rank, world, local, steps, warmup, e2e=True, clocks=True, proc
     # ---------------- end-to-end leg: host buffers in, lnL (+ per-site lnL) out, every step
     e2e_ms = None
     lnl_e2e = lnl
-    e2e_shards = 1
     if e2e:
-        # PLK_BENCH_E2E_SHARDS=k (1 GPU only): the e2e leg runs on an instance whose patterns are split into k blocks
-        # on this same device (plk_create_sharded with the device listed k times): every block has its own stream, so
-        # block j's host-to-device copy overlaps block j-1's traversal inside ONE evaluation
-        e2e_shards = int(os.environ.get("PLK_BENCH_E2E_SHARDS", str(E2E_SHARDS_DEFAULT))) if world == 1 else 1
-        eng_e, evaluate_e = eng, evaluate
-        if e2e_shards > 1:
-            eng_e = Engine(n, P, ns, ncatg, tree.n_clv_handles, tree.n_edges, devices=[local] * e2e_shards)
-            eng_e.set_tip_table(pat.table())
-            evaluate_e = eng_e.lk_full_call(edges, lengths, ops_packed, left, rght, tree.root_edge)
-
-        def upload_inputs_e():
-            if packed:
-                eng_e.set_all_tip_codes_packed4(h_codes)
-            else:
-                eng_e.set_all_tip_codes(h_codes)
-            eng_e.set_weights_ptr(h_wght.data_ptr(), h_invar.data_ptr())
-            eng_e.set_model(m)
-
-        for _ in range(max(2, warmup // 2)):
-            upload_inputs_e()
-            evaluate_e()
-            eng_e.get_site_lnl_ptr(h_site.data_ptr())
+        for _ in range(max(1, warmup // 2)):
+            upload_inputs()
+            evaluate()
+            eng.get_site_lnl_ptr(h_site.data_ptr())
         barrier()
-        launches_e0 = eng_e.launch_count
         t0 = time.perf_counter()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record(stream)
         for s in range(steps):
-            upload_inputs_e()
-            lnl_e2e = evaluate_e()
-            eng_e.get_site_lnl_ptr(h_site.data_ptr())
+            upload_inputs()
+            lnl_e2e = evaluate()
+            eng.get_site_lnl_ptr(h_site.data_ptr())
         g1.record(stream)
         barrier()
         e2e_ms = max(g0.elapsed_time(g1), (time.perf_counter() - t0) * 1e3)
-        e2e_launches = eng_e.launch_count - launches_e0
-        if eng_e is not eng:
-            eng_e.close()
     else:
         eng.get_site_lnl_ptr(h_site.data_ptr())
         eng.sync()
@@ -321,7 +297,6 @@ def measure(name, rank, world, local, steps, warmup, e2e=True, clocks=True, proc
         "name": name, "desc": w.desc, "strong": strong, "n_taxa": n, "ns": ns, "ncatg": ncatg, "P": P, "P_total": P_total,
         "n_sites_total": w.block_sites * (w.n_blocks if strong else world), "blocks": blocks,
         "ms": ms, "steps": steps, "value": updates / (ms * 1e-3), "launches": int(launches), "lnL": lnl,
-        "e2e_shards": e2e_shards, "e2e_launches": int(e2e_launches) if e2e else None,
         "lnL_reference": lnl_ref, "parity_rel_err": parity, "exchange_rel_err": exchange_rel_err,
         "e2e_ms": e2e_ms, "e2e_value": (updates / (e2e_ms * 1e-3)) if e2e_ms else None, "h2d": h2d, "d2h": d2h,
         "k1_bytes": k1_bytes, "k1_ms": k1_avg_ms, "k1_launches": int(k1_launches), "clocks": clk,
@@ -402,8 +377,7 @@ def run_b200(args):
             "parity_rel_err": rec["parity_rel_err"], "parity_rtol": PARITY_RTOL,
             "exchange_rel_err": rec["exchange_rel_err"],
             "e2e": {"value": rec["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": rec["h2d"], "d2h_bytes_per_step": rec["d2h"],
-                    "ms_per_step": rec["e2e_ms"] / args.steps, "pattern_blocks": rec["e2e_shards"],
-                    "gpu_launches": rec["e2e_launches"]},
+                    "ms_per_step": rec["e2e_ms"] / args.steps},
             "gpu_launches": rec["launches"],
             "clocks": rec["clocks"],
             "roofline": roofline_of(rec, peaks),

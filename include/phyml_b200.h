@@ -200,6 +200,29 @@ int plk_comm_set_allreduce(plk_instance *inst, int enable);
 int plk_create_sharded(const plk_config *cfg, int n_gpus, const int *devices, plk_instance **out);
 int plk_n_shards(const plk_instance *inst);
 
+/* ---- batched SPR candidates ------------------------------------------
+ * Test_One_Spr_Target (src/spr.c:589-650) scores ONE regraft position of a pruned subtree: Graft_Subtree,
+ * Update_PMat_At_Given_Edge on the two halves of the target edge, Update_Partial_Lk(tree, b_arrow, n_link),
+ * Lk(b_arrow).  Once the subtree is pruned and the remaining tree's CLVs are up to date on both sides, every such
+ * score depends only on existing buffers, so the scores of ALL regraft positions come from one call:
+ *   a, l_a : CLV (or tip) seen from one end of the target edge, looking away from the regraft point, and the
+ *            length of that half after Graft_Subtree (b_target->l->v);  b, l_b : the other end (b_residual);
+ *   prune, l_prune : the pruned subtree's CLV (or tip) and the length of the edge that carries it (b_arrow);
+ *   link_on_left   : non-zero when the new node n_link is b_arrow->left (always the case when `prune` is a tip).
+ * lnl[i] = what Lk(b_arrow) would return for candidate i (the all-shard sum on a sharded instance); the CLV of
+ * n_link is never written and no per-site by-product is stored.  Using it needs a caller that enumerates the
+ * regraft positions itself (Test_One_Spr_Target_Recur, src/spr.c:525-586, interleaves enumeration and scoring),
+ * i.e. it is outside the symbol-for-symbol drop-in; INTEGRATION.md section 6 shows the change to spr.c. */
+typedef struct plk_spr_cand
+{
+  plk_side a;
+  double   l_a;
+  plk_side b;
+  double   l_b;
+} plk_spr_cand;
+int plk_spr_candidates(plk_instance *inst, plk_side prune, double l_prune, int link_on_left, int n_cand,
+                       const plk_spr_cand *cand, double *lnl, int *numerical_warning);
+
 /* ---- parsimony: the SPR pre-filter (src/pars.c) ----------------------
  * Every edge side owns a parsimony buffer (b->ui_l/pars_l/p_pars_l and ..._r, src/make.c:455-475; the host
  * swaps the three pointers together in Prune_Subtree/Graft_Subtree, src/utilities.c:6268-6278), named here by

@@ -13,6 +13,7 @@
 #include "../../include/phyml_b200.h"
 #include "plk_kernels.cuh"
 #include "plk_pars.cuh"
+#include "plk_spr.cuh"
 
 using namespace plk;
 
@@ -159,6 +160,11 @@ struct plk_instance
   int                *d_site_pars = nullptr;
   bool                pars_site_valid = false;
   bool                wght_integral = true;  // every pattern weight is an integer (plk_set_pattern_weights)
+
+  // batched SPR candidates (plk_spr_candidates): scratch P-matrices, per-block partial sums, results
+  double *d_spr_pmat = nullptr, *d_spr_partials = nullptr, *d_spr_lnl = nullptr;
+  int    *d_spr_warn = nullptr;
+  int     spr_cap = 0;
 
   // scheduling scratch
   std::vector<int> lvl_write, lvl_read, op_level;
@@ -558,6 +564,10 @@ void plk_destroy(plk_instance *inst)
   for (int *p : inst->pars_sank) cudaFree(p);
   cudaFree(inst->d_step_mat);
   cudaFree(inst->d_site_pars);
+  cudaFree(inst->d_spr_pmat);
+  cudaFree(inst->d_spr_partials);
+  cudaFree(inst->d_spr_lnl);
+  cudaFree(inst->d_spr_warn);
   if (inst->h_result) cudaFreeHost(inst->h_result);
   for (int s = 0; s < kStageSlots; ++s)
   {
@@ -2351,3 +2361,113 @@ int plk_get_site_pars(plk_instance *inst, int *site_pars)
 }
 
 }  // extern "C"
+
+// ---- batched SPR candidates (spr.c:589-650 for many regraft positions at once) ----------------------------
+namespace
+{
+constexpr int kSprChunk = 2048;      // candidates per launch
+constexpr int kSprBlocksPerCand = 64;
+
+int spr_ensure(plk_instance *inst)
+{
+  if (inst->spr_cap) return PLK_OK;
+  const size_t pm = (size_t)inst->cfg.ncatg * inst->cfg.ns * inst->cfg.ns;
+  int          rc;
+  if ((rc = dev_alloc(inst, &inst->d_spr_pmat, (size_t)(2 * kSprChunk + 1) * pm))) return rc;
+  if ((rc = dev_alloc(inst, &inst->d_spr_partials, (size_t)kSprChunk * kSprBlocksPerCand))) return rc;
+  if ((rc = dev_alloc(inst, &inst->d_spr_lnl, (size_t)kSprChunk))) return rc;
+  if ((rc = dev_alloc(inst, &inst->d_spr_warn, (size_t)kSprChunk))) return rc;
+  inst->spr_cap = kSprChunk;
+  return PLK_OK;
+}
+
+// one shard / plain instance: lnl[i] += this instance's partial sum for candidate i, warn[i] |= its warning flag
+int spr_candidates_local(plk_instance *inst, plk_side prune, double l_prune, int link_on_left, int n_cand,
+                         const plk_spr_cand *cand, double *lnl, int *warn)
+{
+  USE_DEVICE(inst);
+  int rc = check_side(inst, prune, true);
+  if (rc) return rc;
+  ARG_CHECK(inst, link_on_left || prune.clv >= 0, "plk_spr_candidates: a tip is always the right-hand side of its edge");
+  for (int i = 0; i < n_cand; ++i)
+    if ((rc = check_side(inst, cand[i].a, true)) || (rc = check_side(inst, cand[i].b, true))) return rc;
+  if ((rc = spr_ensure(inst))) return rc;
+  const int    ns = inst->cfg.ns, nc = inst->cfg.ncatg, P = inst->cfg.n_patterns;
+  const size_t pm = (size_t)nc * ns * ns;
+  const int    bpc = std::max(1, std::min(kSprBlocksPerCand, (P + kSprThreads * 4 - 1) / (kSprThreads * 4)));
+  const int    threads = ((ns * ns + 31) / 32) * 32;
+  const size_t smem = (size_t)(kMaxNs + ns * ns) * sizeof(double);
+  std::vector<PmatJob>    jobs;
+  std::vector<SprCandDev> dev;
+  std::vector<double>     h_lnl;
+  std::vector<int>        h_warn;
+  for (int off = 0; off < n_cand; off += kSprChunk)
+  {
+    const int n = std::min(kSprChunk, n_cand - off);
+    // K0 for this chunk: P(l_a), P(l_b) per candidate and P(l_prune) (models.c:257-326, lk.c:2296-2300)
+    jobs.resize((size_t)2 * n + 1);
+    dev.resize((size_t)n);
+    for (int i = 0; i < n; ++i)
+    {
+      jobs[2 * i].P = inst->d_spr_pmat + (size_t)(2 * i) * pm;
+      jobs[2 * i].l = cand[off + i].l_a;
+      jobs[2 * i + 1].P = inst->d_spr_pmat + (size_t)(2 * i + 1) * pm;
+      jobs[2 * i + 1].l = cand[off + i].l_b;
+      dev[i].a = side_dev(inst, cand[off + i].a);
+      dev[i].b = side_dev(inst, cand[off + i].b);
+      dev[i].Pa = jobs[2 * i].P;
+      dev[i].Pb = jobs[2 * i + 1].P;
+    }
+    jobs[2 * n].P = inst->d_spr_pmat + (size_t)(2 * n) * pm;
+    jobs[2 * n].l = l_prune;
+    void *d_jobs = nullptr, *d_cands = nullptr;
+    if ((rc = stage_upload(inst, jobs.data(), sizeof(PmatJob) * jobs.size(), &d_jobs))) return rc;
+    k_pmat<<<(unsigned)(jobs.size() * nc), threads, smem, inst->stream>>>((const PmatJob *)d_jobs, inst->d_model, ns, nc, 0);
+    inst->launches++;
+    CU_TRY(inst, cudaGetLastError());
+    if ((rc = stage_upload(inst, dev.data(), sizeof(SprCandDev) * dev.size(), &d_cands))) return rc;
+    CU_TRY(inst, cudaMemsetAsync(inst->d_spr_warn, 0, sizeof(int) * (size_t)n, inst->stream));
+    k_spr_candidates<<<(unsigned)(n * bpc), kSprThreads, 0, inst->stream>>>(
+        (const SprCandDev *)d_cands, bpc, side_dev(inst, prune), jobs[2 * n].P, link_on_left, inst->d_model, P, ns, nc,
+        inst->d_wght, inst->d_invar, inst->d_tipmask, inst->apply_scaling, inst->blocked, inst->d_spr_partials,
+        inst->d_spr_warn);
+    k_spr_finish<<<(n + 127) / 128, 128, 0, inst->stream>>>(inst->d_spr_partials, bpc, n, inst->d_spr_lnl);
+    inst->launches += 2;
+    CU_TRY(inst, cudaGetLastError());
+    h_lnl.resize((size_t)n);
+    h_warn.resize((size_t)n);
+    CU_TRY(inst, cudaMemcpyAsync(h_lnl.data(), inst->d_spr_lnl, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, inst->stream));
+    CU_TRY(inst, cudaMemcpyAsync(h_warn.data(), inst->d_spr_warn, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, inst->stream));
+    CU_TRY(inst, cudaStreamSynchronize(inst->stream));
+    for (int i = 0; i < n; ++i)
+    {
+      lnl[off + i] += h_lnl[i];
+      if (warn) warn[off + i] |= h_warn[i];
+    }
+  }
+  return PLK_OK;
+}
+}  // namespace
+
+extern "C" int plk_spr_candidates(plk_instance *inst, plk_side prune, double l_prune, int link_on_left, int n_cand,
+                                  const plk_spr_cand *cand, double *lnl, int *numerical_warning)
+{
+  ARG_CHECK(inst, n_cand >= 0 && (n_cand == 0 || (cand && lnl)), "plk_spr_candidates: bad arguments");
+  if (inst->world > 1 || inst->allreduce)
+  {
+    inst->err = "plk_spr_candidates: not available on an instance that is one rank of a multi-process job";
+    return PLK_ERR_UNSUPPORTED;
+  }
+  for (int i = 0; i < n_cand; ++i)
+  {
+    lnl[i] = 0.0;
+    if (numerical_warning) numerical_warning[i] = 0;
+  }
+  if (n_cand == 0) return PLK_OK;
+  if (!inst->shards.empty())
+  {  // all-shard sums, added in shard order
+    FOR_SHARDS(inst, spr_candidates_local(sh, prune, l_prune, link_on_left, n_cand, cand, lnl, numerical_warning));
+    return PLK_OK;
+  }
+  return spr_candidates_local(inst, prune, l_prune, link_on_left, n_cand, cand, lnl, numerical_warning);
+}

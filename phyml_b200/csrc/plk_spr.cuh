@@ -1,0 +1,211 @@
+// phyml_b200/csrc/plk_spr.cuh -- batched evaluation of SPR regraft candidates.
+//
+// The reference scores the regraft positions of one pruned subtree one at a time (Test_One_Spr_Target,
+// src/spr.c:589-650): Graft_Subtree, two Update_PMat_At_Given_Edge, one Update_Partial_Lk at the new node n_link,
+// one Lk(b_arrow) -- a host round trip per candidate.  Every one of those scores depends only on state that exists
+// once the subtree has been pruned (the CLVs seen from both ends of every target edge and the CLV of the pruned
+// subtree), so all candidates can be scored in ONE launch:
+//
+//   k_spr_candidates   grid = candidates x site blocks.  Per (candidate, pattern): the CLV of the new node
+//                      X = (P(l_a) . A) o (P(l_b) . B) with the 2^256 rescaling of avx.c:460-513, then the site
+//                      likelihood across the pruned edge, sum_k pi_k R_k sum_l P(l_prune)_kl L_l (+I, scalers), exactly
+//                      the arithmetic of one K1 update followed by one K2 site loop -- X never goes to memory.
+//   k_spr_finish       per candidate: adds the per-block partial sums in block order (deterministic).
+//
+// Per candidate the kernel reads two CLVs (+ the pruned subtree's CLV, shared by all candidates and L2-resident) and
+// writes a handful of doubles: HBM-bound, 2 x 8 x ns x ncatg bytes per (candidate, pattern).
+#pragma once
+#include "plk_kernels.cuh"
+
+namespace plk
+{
+
+struct SprCandDev
+{
+  SideDev       a, b;    // the two ends of the target edge, each looking away from the regraft point
+  const double *Pa, *Pb; // P(l_a), P(l_b): [ncatg][ns][ns]
+};
+
+constexpr int kSprThreads = 128;
+
+// vector seen through P from one child at (site, category c): an internal CLV (any layout) or a tip mask
+__device__ __forceinline__ void spr_child(const SideDev &s, const double *__restrict__ Pc, uint32_t mask, int site, int c,
+                                          int ns, int ncatg, int blocked, double *__restrict__ u, bool *ones)
+{
+  double v[kMaxNs];
+  if (s.clv)
+  {
+    bool o = true;
+    for (int j = 0; j < ns; ++j)
+    {
+      v[j] = s.clv[clv_off(site, c, j, ncatg, ns, blocked)];
+      o = o && (v[j] == 1.0);
+    }
+    *ones = o;
+  }
+  else
+    *ones = (mask == ((ns >= 32) ? 0xffffffffu : ((1u << ns) - 1u)));
+  for (int i = 0; i < ns; ++i) u[i] = child_dot(Pc + i * ns, v, mask, s.clv != nullptr, ns);
+}
+
+__global__ void __launch_bounds__(kSprThreads)
+    k_spr_candidates(const SprCandDev *__restrict__ cands, int blocks_per_cand, SideDev prune,
+                     const double *__restrict__ Pp, int link_on_left, const ModelDev *__restrict__ mod, int npat, int ns,
+                     int ncatg, const double *__restrict__ wght, const short *__restrict__ invar,
+                     const uint32_t *__restrict__ tipmask, int apply_scaling, int blocked,
+                     double *__restrict__ partials, int *__restrict__ warn_out)
+{
+  const int        cand = blockIdx.x / blocks_per_cand, blk = blockIdx.x % blocks_per_cand;
+  const SprCandDev cd = cands[cand];
+  const int        nn = ns * ns;
+  const double    *pi = mod->pi;
+  const double     big = two_to_large(), small = inv_two_to_large();
+  double           acc = 0.0;
+  int              warn = 0;
+
+  for (int site = blk * blockDim.x + threadIdx.x; site < npat; site += blocks_per_cand * blockDim.x)
+  {
+    const double w = wght[site];
+    if (!(w > DBL_MIN)) continue;  // lk.c:632, avx.c:399
+    const uint32_t ma = cd.a.clv ? 0u : tipmask[cd.a.tip[site]];
+    const uint32_t mb = cd.b.clv ? 0u : tipmask[cd.b.tip[site]];
+    const uint32_t mp = prune.clv ? 0u : tipmask[prune.tip[site]];
+    double         ua[kMaxNs], ub[kMaxNs], x[kMaxNs];
+    bool           oa, ob;
+
+    // pass 1: the largest entry of the new node's CLV decides the 2^256 rescaling (avx.c:460-513)
+    double largest = -DBL_MAX;
+    for (int c = 0; c < ncatg; ++c)
+    {
+      spr_child(cd.a, cd.Pa + (size_t)c * nn, ma, site, c, ns, ncatg, blocked, ua, &oa);
+      spr_child(cd.b, cd.Pb + (size_t)c * nn, mb, site, c, ns, ncatg, blocked, ub, &ob);
+      for (int i = 0; i < ns; ++i) largest = fmax(largest, (oa && ob) ? 1.0 : ua[i] * ub[i]);
+    }
+    const bool rescale = (largest < small) && apply_scaling;
+    const int  sx = (cd.a.scale ? cd.a.scale[site] : 0) + (cd.b.scale ? cd.b.scale[site] : 0) + (rescale ? kLarge : 0);
+
+    // pass 2: per category, the new node's CLV again and the site likelihood across the pruned edge
+    const bool right_is_tip = link_on_left && !prune.clv;
+    const bool unamb = right_is_tip && (__popc(mp) == 1);  // lk.c:614-621
+    const int  st = unamb ? (__ffs(mp) - 1) : -1;
+    double     site_lk = 0.0;
+    for (int c = 0; c < ncatg; ++c)
+    {
+      spr_child(cd.a, cd.Pa + (size_t)c * nn, ma, site, c, ns, ncatg, blocked, ua, &oa);
+      spr_child(cd.b, cd.Pb + (size_t)c * nn, mb, site, c, ns, ncatg, blocked, ub, &ob);
+      for (int i = 0; i < ns; ++i)
+      {
+        double o = (oa && ob) ? 1.0 : ua[i] * ub[i];
+        if (rescale) o *= big;
+        x[i] = o;
+      }
+      const double *Pc = Pp + (size_t)c * nn;
+      auto          PV = [&](int k) -> double {
+        return prune.clv ? prune.clv[clv_off(site, c, k, ncatg, ns, blocked)] : (double)((mp >> k) & 1u);
+      };
+      auto LV = [&](int l) -> double { return link_on_left ? x[l] : PV(l); };
+      auto RV = [&](int k) -> double { return link_on_left ? PV(k) : x[k]; };
+      double lk;
+      if ((ns & 3) == 0)
+      {  // order of AVX_Lk_Core_One_Class_No_Eigen_Lr (avx.c:110-215), as k_edge_lnl
+        if (unamb)
+        {
+          double q[4] = {0.0, 0.0, 0.0, 0.0};
+          for (int b4 = 0; b4 < ns; b4 += 4)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) q[t] = q[t] + Pc[st * ns + b4 + t] * LV(b4 + t);
+          lk = pi[st] * hsum4(q[0], q[1], q[2], q[3]);
+        }
+        else
+        {
+          lk = 0.0;
+          for (int b4 = 0; b4 < ns; b4 += 4)
+          {
+            double y[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+            {
+              const int    k = b4 + t;
+              const double rv = RV(k);
+              double       a = 0.0;
+              for (int l = 0; l < ns; ++l) a = fma(Pc[k * ns + l], LV(l), a);
+              y[t] = a * (rv * pi[k]);
+            }
+            lk = lk + hsum4(y[0], y[1], y[2], y[3]);
+          }
+        }
+      }
+      else
+      {  // scalar order, lk.c:1185-1218
+        lk = 0.0;
+        if (unamb)
+        {
+          double sum = 0.0;
+          for (int l = 0; l < ns; ++l) sum = sum + Pc[st * ns + l] * LV(l);
+          lk = sum * pi[st];
+        }
+        else
+          for (int k = 0; k < ns; ++k)
+          {
+            const double rv = RV(k);
+            if (rv > 0.0)
+            {
+              double sum = 0.0;
+              for (int l = 0; l < ns; ++l) sum = sum + Pc[k * ns + l] * LV(l);
+              lk = lk + sum * pi[k] * rv;
+            }
+          }
+      }
+      site_lk = site_lk + lk * mod->probs[c];  // lk.c:818
+    }
+    int fact = sx + (prune.scale ? prune.scale[site] : 0);  // lk.c:2781-2791
+    if (mod->invar_flag)
+    {  // lk.c:820-842
+      bool   ovf;
+      double inv = invariant_lk(fact, invar[site], pi, &ovf);
+      if (ovf)
+      {
+        fact = 0;
+        inv = invariant_lk(0, invar[site], pi, &ovf);
+        site_lk = inv * mod->pinv;
+      }
+      else
+        site_lk = site_lk * (1. - mod->pinv) + inv * mod->pinv;
+    }
+    if (site_lk < DBL_MIN)
+    {
+      site_lk = DBL_MIN;
+      warn = 1;
+    }
+    acc += w * (log(site_lk) - kLog2 * fact);  // lk.c:854-856
+  }
+
+  // block sum: fixed shuffle tree, fixed warp order
+  __shared__ double sred[kSprThreads / 32];
+  __shared__ int    swarn;
+  if (threadIdx.x == 0) swarn = 0;
+  __syncthreads();
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = acc;
+  if (warn) atomicOr(&swarn, 1);
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    double s = 0.0;
+    for (int wq = 0; wq < kSprThreads / 32; ++wq) s += sred[wq];
+    partials[(size_t)cand * blocks_per_cand + blk] = s;
+    if (swarn) atomicOr(&warn_out[cand], 1);
+  }
+}
+
+__global__ void k_spr_finish(const double *__restrict__ partials, int blocks_per_cand, int n_cand, double *__restrict__ lnl)
+{
+  const int cand = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cand >= n_cand) return;
+  double s = 0.0;
+  for (int b = 0; b < blocks_per_cand; ++b) s += partials[(size_t)cand * blocks_per_cand + b];
+  lnl[cand] = s;
+}
+
+}  // namespace plk

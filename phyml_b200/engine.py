@@ -35,6 +35,10 @@ class _Op(C.Structure):
     _fields_ = [("dst", C.c_int), ("c1", _Side), ("pmat1", C.c_int), ("c2", _Side), ("pmat2", C.c_int)]
 
 
+class _SprCand(C.Structure):
+    _fields_ = [("a", _Side), ("l_a", C.c_double), ("b", _Side), ("l_b", C.c_double)]
+
+
 OP_DTYPE = np.dtype([("dst", "<i4"), ("c1_tip", "<i4"), ("c1_clv", "<i4"), ("pmat1", "<i4"),
                      ("c2_tip", "<i4"), ("c2_clv", "<i4"), ("pmat2", "<i4")])
 assert OP_DTYPE.itemsize == C.sizeof(_Op)
@@ -48,7 +52,7 @@ EXPORTS = [
     "plk_comm_p2p_export", "plk_comm_p2p_init", "plk_create_sharded", "plk_n_shards",
     "plk_launch_count", "plk_device_bytes", "plk_stream", "plk_version",
     "plk_pars_create", "plk_pars_set_buffer", "plk_pars_get_buffer", "plk_pars_update", "plk_pars_edge",
-    "plk_pars_traverse_edge", "plk_get_site_pars",
+    "plk_pars_traverse_edge", "plk_get_site_pars", "plk_spr_candidates",
 ]
 
 _lib = None
@@ -113,6 +117,7 @@ def load_library() -> C.CDLL:
     lib.plk_pars_edge.argtypes = [vp, C.c_int, C.c_int, C.c_int, ip]
     lib.plk_pars_traverse_edge.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, ip]
     lib.plk_get_site_pars.argtypes = [vp, vp]
+    lib.plk_spr_candidates.argtypes = [vp, _Side, C.c_double, C.c_int, C.c_int, vp, vp, vp]
     _lib = lib
     return lib
 
@@ -358,6 +363,19 @@ class Engine:
         out = np.empty((self.P, self.ncatg, self.ns))
         self._ck(self.lib.plk_get_dot_prod(self.h, _ptr(out)))
         return out
+
+    # ------------------------------------------------------------------ batched SPR candidates
+    def spr_candidates(self, prune: Side, l_prune: float, link_on_left: bool, cands):
+        """Scores of many regraft positions of one pruned subtree in one call (``plk_spr_candidates``).
+        ``cands``: sequence of (Side a, l_a, Side b, l_b).  Returns (lnl array, warning flags)."""
+        arr = (_SprCand * max(1, len(cands)))()
+        for i, (a, la, b, lb) in enumerate(cands):
+            arr[i] = _SprCand(_Side(a.tip, a.clv), float(la), _Side(b.tip, b.clv), float(lb))
+        lnl = np.zeros(len(cands))
+        warn = np.zeros(len(cands), dtype=np.int32)
+        self._ck(self.lib.plk_spr_candidates(self.h, _Side(prune.tip, prune.clv), float(l_prune), int(bool(link_on_left)),
+                                             len(cands), C.cast(arr, C.c_void_p), _ptr(lnl), _ptr(warn)))
+        return lnl, warn
 
     # ------------------------------------------------------------------ parsimony (src/pars.c)
     def pars_create(self, n_buffers: int, step_mat=None):

@@ -198,6 +198,24 @@ class OracleBackend:
     def get_dot_prod(self):
         return self.dot_prod.copy()
 
+    # ---- batched SPR candidates: the sequential composition the batched call stands for (spr.c:589-650)
+    def spr_candidates(self, prune, l_prune, link_on_left, cands):
+        from phyml_b200.tree import PartialOp, Side
+        keep_pm = self.pm
+        self.pm = np.concatenate([keep_pm, np.zeros((3,) + keep_pm.shape[1:])])
+        ha, hb, hp = len(keep_pm), len(keep_pm) + 1, len(keep_pm) + 2
+        tmp = -12345
+        lnl, warn = np.zeros(len(cands)), np.zeros(len(cands), dtype=np.int32)
+        for i, (a, la, b, lb) in enumerate(cands):
+            self.update_pmats([ha, hb, hp], [la, lb, l_prune])
+            self.update_partials([PartialOp(dst=tmp, c1=a, pmat1=ha, c2=b, pmat2=hb)])
+            x = Side(clv=tmp)
+            lnl[i] = self.edge_lnl(x, prune, hp) if link_on_left else self.edge_lnl(prune, x, hp)
+            warn[i] = self.numerical_warning
+        del self.clv[tmp], self.scale[tmp]
+        self.pm = keep_pm
+        return lnl, warn
+
     # ---- parsimony (oracle restatement of src/pars.c)
     def pars_create(self, n_buffers, step_mat=None):
         self.step_mat = None if step_mat is None else np.ascontiguousarray(step_mat, dtype=np.int32)

@@ -54,5 +54,15 @@ res["Br_Len_Opt (Lk(b)+eigen_lr+~20 dLk+pmat)"] = timeit(lambda: t.Br_Len_Opt(e)
 full = pack_ops(tree.post_order_ops())
 res["Lk(NULL) post-order"] = timeit(lambda: (eng.update_pmats(np.arange(tree.n_edges, dtype=np.int32), tree.l),
                                              eng.update_partials(full), eng.edge_lnl(*tree.edge_sides(tree.root_edge), tree.root_edge)), n=50)
+# all regraft positions of one pruned subtree in ONE call (plk_spr_candidates) vs one call sequence per candidate
+tip = 3
+te = tree.adj[tip][0][0]
+cands = []
+for ee in range(tree.n_edges):
+    if ee != te:
+        a, b = tree.edge_sides(ee)
+        cands.append((a, 0.5 * tree.l[ee], b, 0.5 * tree.l[ee]))
+t_batch = timeit(lambda: eng.spr_candidates(tree.side_of(te, tip), float(tree.l[te]), True, cands), n=20, warm=3)
+res["plk_spr_candidates: %d candidates in one call, per candidate" % len(cands)] = t_batch / len(cands)
 for k, v in res.items():
     print(f"{v:10.1f} us  {k}")
