@@ -183,6 +183,7 @@ struct plk_instance
     if (e_ != cudaSuccess)                                                                         \
     {                                                                                              \
       (inst)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                            \
+      (void)cudaGetLastError(); /* a non-sticky error must not surface again in a later call */    \
       return PLK_ERR_CUDA;                                                                         \
     }                                                                                              \
   } while (0)
@@ -987,8 +988,9 @@ static int launch_traverse_aa(plk_instance *inst, const OpDev *d_ops, int n_ops)
     case 1: return launch_traverse_aa3_t<1>(inst, d_ops, n_ops);
     case 2: return launch_traverse_aa3_t<2>(inst, d_ops, n_ops);
     case 4: return launch_traverse_aa3_t<4>(inst, d_ops, n_ops);
-    case 8: return launch_traverse_aa3_t<8>(inst, d_ops, n_ops);
     }
+  // other category counts (3, 5..8): the first-generation kernel, whose 3 stages fit shared memory up to ncatg = 8
+  // (4 stages of Aa3Stage<8> would need 460 KB)
   const int    nc = inst->cfg.ncatg, P = inst->cfg.n_patterns;
   const size_t smem = (size_t)kAaStages * aa_stage_bytes(nc);
   if (!inst->aa_attr_set)
@@ -1627,9 +1629,15 @@ int plk_eigen_lr(plk_instance *inst, plk_side left, plk_side rght)
   }
   const long long work = (long long)inst->cfg.n_patterns * inst->cfg.ncatg;
   const int       grid = (int)std::max<long long>(1, std::min<long long>((work + 127) / 128, inst->num_sms * 32));
-  k_eigen_lr<<<grid, 128, 0, inst->stream>>>(side_dev(inst, left), side_dev(inst, rght), inst->d_model,
-                                             inst->cfg.n_patterns, inst->cfg.ns, inst->cfg.ncatg, inst->d_wght,
-                                             inst->d_tipmask, inst->d_dot_prod, inst->d_fact, inst->blocked);
+  static const bool generic_k3 = getenv("PLK_K3_GENERIC") != nullptr;
+  if (inst->cfg.ns == 20 && !generic_k3)
+    k_eigen_lr_reg<20><<<grid, 128, 0, inst->stream>>>(side_dev(inst, left), side_dev(inst, rght), inst->d_model,
+                                                       inst->cfg.n_patterns, inst->cfg.ncatg, inst->d_wght,
+                                                       inst->d_tipmask, inst->d_dot_prod, inst->d_fact, inst->blocked);
+  else
+    k_eigen_lr<<<grid, 128, 0, inst->stream>>>(side_dev(inst, left), side_dev(inst, rght), inst->d_model,
+                                               inst->cfg.n_patterns, inst->cfg.ns, inst->cfg.ncatg, inst->d_wght,
+                                               inst->d_tipmask, inst->d_dot_prod, inst->d_fact, inst->blocked);
   inst->launches++;
   CU_TRY(inst, cudaGetLastError());
   inst->eigen_ready = true;
@@ -2427,10 +2435,16 @@ int spr_candidates_local(plk_instance *inst, plk_side prune, double l_prune, int
     CU_TRY(inst, cudaGetLastError());
     if ((rc = stage_upload(inst, dev.data(), sizeof(SprCandDev) * dev.size(), &d_cands))) return rc;
     CU_TRY(inst, cudaMemsetAsync(inst->d_spr_warn, 0, sizeof(int) * (size_t)n, inst->stream));
-    k_spr_candidates<<<(unsigned)(n * bpc), kSprThreads, 0, inst->stream>>>(
-        (const SprCandDev *)d_cands, bpc, side_dev(inst, prune), jobs[2 * n].P, link_on_left, inst->d_model, P, ns, nc,
-        inst->d_wght, inst->d_invar, inst->d_tipmask, inst->apply_scaling, inst->blocked, inst->d_spr_partials,
-        inst->d_spr_warn);
+    static const bool generic_spr = getenv("PLK_SPR_GENERIC") != nullptr;
+    if (inst->fused_dna && nc == 4 && !generic_spr)
+      k_spr_candidates_dna4<<<(unsigned)(n * bpc), kSprThreads, 0, inst->stream>>>(
+          (const SprCandDev *)d_cands, bpc, side_dev(inst, prune), jobs[2 * n].P, link_on_left, inst->d_model, P,
+          inst->d_wght, inst->d_invar, inst->d_tipmask, inst->apply_scaling, inst->d_spr_partials, inst->d_spr_warn);
+    else
+      k_spr_candidates<<<(unsigned)(n * bpc), kSprThreads, 0, inst->stream>>>(
+          (const SprCandDev *)d_cands, bpc, side_dev(inst, prune), jobs[2 * n].P, link_on_left, inst->d_model, P, ns, nc,
+          inst->d_wght, inst->d_invar, inst->d_tipmask, inst->apply_scaling, inst->blocked, inst->d_spr_partials,
+          inst->d_spr_warn);
     k_spr_finish<<<(n + 127) / 128, 128, 0, inst->stream>>>(inst->d_spr_partials, bpc, n, inst->d_spr_lnl);
     inst->launches += 2;
     CU_TRY(inst, cudaGetLastError());

@@ -3552,6 +3552,71 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// K3 with the state count known at compile time (20 states): thread per (site, category) as above, but both
+// conditional vectors live in registers (read from global memory once instead of once per output state) and U
+// (transposed, so that the j-loop walks contiguous words) and V come from shared memory as warp-wide broadcasts.
+// Same products and the same FMA chains as k_eigen_lr, i.e. bit-identical dot_prod.
+template <int NS>
+__global__ void __launch_bounds__(128)
+    k_eigen_lr_reg(SideDev left, SideDev rght, const ModelDev *__restrict__ mod, int npat, int ncatg,
+                   const double *__restrict__ wght, const uint32_t *__restrict__ tipmask, double *__restrict__ dot_prod,
+                   int *__restrict__ fact_sum_scale, int blocked)
+{
+  __shared__ double sUt[NS * NS], sV[NS * NS], sPi[NS];
+  for (int t = threadIdx.x; t < NS * NS; t += blockDim.x)
+  {
+    sUt[(t % NS) * NS + (t / NS)] = mod->U[t];  // sUt[i][j] = U[j][i]
+    sV[t] = mod->V[t];
+  }
+  if (threadIdx.x < NS) sPi[threadIdx.x] = mod->pi[threadIdx.x];
+  __syncthreads();
+  const int       ncns = ncatg * NS;
+  const long long total = (long long)npat * ncatg;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x)
+  {
+    const int site = (int)(g / ncatg), c = (int)(g % ncatg);
+    if (c == 0) fact_sum_scale[site] = (left.scale ? left.scale[site] : 0) + (rght.scale ? rght.scale[site] : 0);
+    if (!(wght[site] > DBL_MIN)) continue;  // lk.c:1082
+    double lv[NS], rv[NS];
+    if (left.clv)
+    {
+#pragma unroll
+      for (int j = 0; j < NS; ++j) lv[j] = left.clv[clv_off(site, c, j, ncatg, NS, blocked)] * sPi[j];
+    }
+    else
+    {
+      const uint32_t lm = tipmask[left.tip[site]];
+#pragma unroll
+      for (int j = 0; j < NS; ++j) lv[j] = (double)((lm >> j) & 1u) * sPi[j];
+    }
+    if (rght.clv)
+    {
+#pragma unroll
+      for (int j = 0; j < NS; ++j) rv[j] = rght.clv[clv_off(site, c, j, ncatg, NS, blocked)];
+    }
+    else
+    {
+      const uint32_t rm = tipmask[rght.tip[site]];
+#pragma unroll
+      for (int j = 0; j < NS; ++j) rv[j] = (double)((rm >> j) & 1u);
+    }
+    double *o = dot_prod + (size_t)site * ncns + c * NS;
+#pragma unroll 2
+    for (int i = 0; i < NS; ++i)
+    {  // avx.c:79-84
+      double a = sUt[i * NS] * lv[0];
+      double b = sV[i * NS] * rv[0];
+#pragma unroll
+      for (int j = 1; j < NS; ++j)
+      {
+        a = fma(sUt[i * NS + j], lv[j], a);
+        b = fma(sV[i * NS + j], rv[j], b);
+      }
+      o[i] = a * b;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K4: thread per site.  expl = (E,D) interleaved per category like tree->expl (lk.c:717-725).
 __global__ void __launch_bounds__(128)

@@ -199,6 +199,219 @@ __global__ void __launch_bounds__(kSprThreads)
   }
 }
 
+// matvec4 / tipvec4 of plk_kernels.cuh with the matrix read straight from shared memory (short register lifetimes)
+__device__ __forceinline__ void spr_matvec4(const double *__restrict__ p, const double4a &v, double (&u)[4])
+{
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+  {
+    double a = p[i * 4 + 0] * v.x;
+    a = fma(p[i * 4 + 1], v.y, a);
+    a = fma(p[i * 4 + 2], v.z, a);
+    a = fma(p[i * 4 + 3], v.w, a);
+    u[i] = a;
+  }
+}
+__device__ __forceinline__ void spr_tipvec4(const double *__restrict__ p, uint32_t m, double (&u)[4])
+{
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+  {
+    double a = (m & 1u) ? p[i * 4 + 0] : 0.0;
+    if (m & 2u) a = a + p[i * 4 + 1];
+    if (m & 4u) a = a + p[i * 4 + 2];
+    if (m & 8u) a = a + p[i * 4 + 3];
+    u[i] = a;
+  }
+}
+
+// 4 states, 4 categories on the blocked layout: thread per (pattern, category) with the lane map of the traversal
+// kernels (lane = category * 8 + pattern % 8), so a warp reads 1 KB contiguous of every CLV (256-bit loads); the three
+// P-matrices of the block's candidate sit in shared memory (quarter-warp broadcasts); the new node's conditional vector
+// (4 doubles per lane) never leaves registers; the per-pattern maximum (rescaling) and the sum over categories (in
+// category order, as lk.c:818) are shuffles over the 4 lanes of a pattern.  Same products, FMA chains and summation
+// order as k_spr_candidates, i.e. the same per-pattern values bit for bit.
+__global__ void __launch_bounds__(kSprThreads)
+    k_spr_candidates_dna4(const SprCandDev *__restrict__ cands, int blocks_per_cand, SideDev prune,
+                          const double *__restrict__ Pp, int link_on_left, const ModelDev *__restrict__ mod, int npat,
+                          const double *__restrict__ wght, const short *__restrict__ invar,
+                          const uint32_t *__restrict__ tipmask, int apply_scaling, double *__restrict__ partials,
+                          int *__restrict__ warn_out)
+{
+  constexpr int NCATG = 4;
+  __shared__ double sP[3][NCATG * 16];
+  __shared__ double sPi[4], sProb[NCATG];
+  const int        cand = blockIdx.x / blocks_per_cand, blk = blockIdx.x % blocks_per_cand;
+  const SprCandDev cd = cands[cand];
+  for (int t = threadIdx.x; t < NCATG * 16; t += blockDim.x)
+  {
+    sP[0][t] = cd.Pa[t];
+    sP[1][t] = cd.Pb[t];
+    sP[2][t] = Pp[t];
+  }
+  if (threadIdx.x < 4) sPi[threadIdx.x] = mod->pi[threadIdx.x];
+  if (threadIdx.x < NCATG) sProb[threadIdx.x] = mod->probs[threadIdx.x];
+  __syncthreads();
+  const double big = two_to_large(), small = inv_two_to_large();
+  const int    lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int    c = lane >> 3, r = lane & 7;
+  const int    n_groups = (npat + 7) >> 3;
+  double       acc = 0.0;
+  int          warn = 0;
+
+  for (int grp = blk * wpb + warp; grp < n_groups; grp += blocks_per_cand * wpb)
+  {
+    const int    site = grp * 8 + r;
+    const bool   in = site < npat;
+    const double w = in ? wght[site] : 0.0;
+    const bool   live = in && (w > DBL_MIN);  // lk.c:632, avx.c:399 (the 4 lanes of a pattern agree)
+    const size_t off = ((size_t)grp * NCATG + c) * 32 + r * 4;
+    double       x[4] = {0.0, 0.0, 0.0, 0.0};
+    int          sx = 0;
+    uint32_t     mp = 0u;
+    if (live)
+    {
+      double ua[4], ub[4];
+      bool   oa, ob;
+      if (cd.a.clv)
+      {
+        const double4a v = ld256(cd.a.clv + off);
+        oa = all_one(v);
+        spr_matvec4(sP[0] + c * 16, v, ua);
+        sx += cd.a.scale[site];
+      }
+      else
+      {
+        const uint32_t ma = tipmask[cd.a.tip[site]];
+        oa = (ma == 15u);
+        spr_tipvec4(sP[0] + c * 16, ma, ua);
+      }
+      if (cd.b.clv)
+      {
+        const double4a v = ld256(cd.b.clv + off);
+        ob = all_one(v);
+        spr_matvec4(sP[1] + c * 16, v, ub);
+        sx += cd.b.scale[site];
+      }
+      else
+      {
+        const uint32_t mb = tipmask[cd.b.tip[site]];
+        ob = (mb == 15u);
+        spr_tipvec4(sP[1] + c * 16, mb, ub);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) x[i] = (oa && ob) ? 1.0 : ua[i] * ub[i];
+      if (!prune.clv) mp = tipmask[prune.tip[site]];
+    }
+    // largest entry of the new node's CLV over its 4 states x 4 categories (avx.c:460-513)
+    double largest = fmax(fmax(x[0], x[1]), fmax(x[2], x[3]));
+    largest = fmax(largest, __shfl_xor_sync(0xffffffffu, largest, 8));
+    largest = fmax(largest, __shfl_xor_sync(0xffffffffu, largest, 16));
+    const bool rescale = (largest < small) && apply_scaling;
+    if (rescale)
+    {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) x[i] *= big;
+      sx += kLarge;
+    }
+    double term = 0.0;
+    if (live)
+    {
+      double pv[4];
+      if (prune.clv)
+      {
+        const double4a v = ld256(prune.clv + off);
+        pv[0] = v.x, pv[1] = v.y, pv[2] = v.z, pv[3] = v.w;
+      }
+      else
+      {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pv[k] = (double)((mp >> k) & 1u);
+      }
+      double L[4], R[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+      {
+        L[k] = link_on_left ? x[k] : pv[k];
+        R[k] = link_on_left ? pv[k] : x[k];
+      }
+      const double *Pc = sP[2] + c * 16;
+      const bool    unamb = link_on_left && !prune.clv && (__popc(mp) == 1);  // lk.c:614-621
+      double        lk;
+      if (unamb)
+      {
+        const int st = __ffs(mp) - 1;
+        double    q[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) q[t] = 0.0 + Pc[st * 4 + t] * L[t];
+        lk = sPi[st] * hsum4(q[0], q[1], q[2], q[3]);
+      }
+      else
+      {
+        double y[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+          double a = 0.0;
+#pragma unroll
+          for (int l = 0; l < 4; ++l) a = fma(Pc[k * 4 + l], L[l], a);
+          y[k] = a * (R[k] * sPi[k]);
+        }
+        lk = 0.0 + hsum4(y[0], y[1], y[2], y[3]);
+      }
+      term = lk * sProb[c];
+    }
+    // site_lk = ((0 + t0) + t1) + t2) + t3, lk.c:818
+    const double t1 = __shfl_sync(0xffffffffu, term, r + 8);
+    const double t2 = __shfl_sync(0xffffffffu, term, r + 16);
+    const double t3 = __shfl_sync(0xffffffffu, term, r + 24);
+    if (live && c == 0)
+    {
+      double site_lk = 0.0 + term;
+      site_lk = site_lk + t1;
+      site_lk = site_lk + t2;
+      site_lk = site_lk + t3;
+      int fact = sx + (prune.scale ? prune.scale[site] : 0);
+      if (mod->invar_flag)
+      {
+        bool   ovf;
+        double inv = invariant_lk(fact, invar[site], mod->pi, &ovf);
+        if (ovf)
+        {
+          fact = 0;
+          inv = invariant_lk(0, invar[site], mod->pi, &ovf);
+          site_lk = inv * mod->pinv;
+        }
+        else
+          site_lk = site_lk * (1. - mod->pinv) + inv * mod->pinv;
+      }
+      if (site_lk < DBL_MIN)
+      {
+        site_lk = DBL_MIN;
+        warn = 1;
+      }
+      acc += w * (log(site_lk) - kLog2 * fact);
+    }
+  }
+
+  __shared__ double sred[kSprThreads / 32];
+  __shared__ int    swarn;
+  if (threadIdx.x == 0) swarn = 0;
+  __syncthreads();
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = acc;
+  if (warn) atomicOr(&swarn, 1);
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    double s = 0.0;
+    for (int wq = 0; wq < kSprThreads / 32; ++wq) s += sred[wq];
+    partials[(size_t)cand * blocks_per_cand + blk] = s;
+    if (swarn) atomicOr(&warn_out[cand], 1);
+  }
+}
+
 __global__ void k_spr_finish(const double *__restrict__ partials, int blocks_per_cand, int n_cand, double *__restrict__ lnl)
 {
   const int cand = blockIdx.x * blockDim.x + threadIdx.x;

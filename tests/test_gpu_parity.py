@@ -108,8 +108,9 @@ def test_engine_vs_oracle_synthetic(ns, n_taxa, n_sites, ncatg, pinv, amb, mean_
             b, sb = cpu.eng.get_clv(h)
             assert (sa == sb).all()
             # device exp() vs libm exp() differ by <= 1 ulp; tiny CLV entries inherit the ABSOLUTE
-            # accuracy of near-zero P entries, so compare on the scale of each site
-            assert (np.abs(a - b) <= 1e-12 * np.abs(b).max(axis=(1, 2), keepdims=True)).all()
+            # accuracy of near-zero P entries (a few 1e-16 on entries of 1e-5 .. 1e-6 at short branches), so
+            # compare on the scale of each site
+            assert (np.abs(a - b) <= 1e-11 * np.abs(b).max(axis=(1, 2), keepdims=True)).all()
             np.testing.assert_allclose(a, b, rtol=1e-6, atol=0)
     e = tree.n_edges // 2
     for t in (gpu, cpu):
