@@ -165,6 +165,7 @@ struct plk_instance
   double *d_spr_pmat = nullptr, *d_spr_partials = nullptr, *d_spr_lnl = nullptr;
   int    *d_spr_warn = nullptr;
   int     spr_cap = 0;
+  bool    spr_attr_set = false;
 
   // scheduling scratch
   std::vector<int> lvl_write, lvl_read, op_level;
@@ -2440,6 +2441,18 @@ int spr_candidates_local(plk_instance *inst, plk_side prune, double l_prune, int
       k_spr_candidates_dna4<<<(unsigned)(n * bpc), kSprThreads, 0, inst->stream>>>(
           (const SprCandDev *)d_cands, bpc, side_dev(inst, prune), jobs[2 * n].P, link_on_left, inst->d_model, P,
           inst->d_wght, inst->d_invar, inst->d_tipmask, inst->apply_scaling, inst->d_spr_partials, inst->d_spr_warn);
+    else if (inst->fused_aa && nc == 4 && !generic_spr)
+    {
+      const size_t sm20 = (size_t)(3 * 4 * (20 * 20 + 2) + 20 + 4) * sizeof(double);
+      if (!inst->spr_attr_set)
+      {
+        CU_TRY(inst, cudaFuncSetAttribute(k_spr_candidates_reg4<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm20));
+        inst->spr_attr_set = true;
+      }
+      k_spr_candidates_reg4<20><<<(unsigned)(n * bpc), kSprThreads, sm20, inst->stream>>>(
+          (const SprCandDev *)d_cands, bpc, side_dev(inst, prune), jobs[2 * n].P, link_on_left, inst->d_model, P,
+          inst->d_wght, inst->d_invar, inst->d_tipmask, inst->apply_scaling, inst->d_spr_partials, inst->d_spr_warn);
+    }
     else
       k_spr_candidates<<<(unsigned)(n * bpc), kSprThreads, 0, inst->stream>>>(
           (const SprCandDev *)d_cands, bpc, side_dev(inst, prune), jobs[2 * n].P, link_on_left, inst->d_model, P, ns, nc,

@@ -412,6 +412,254 @@ __global__ void __launch_bounds__(kSprThreads)
   }
 }
 
+// child_dot with the state count known at compile time (the vector stays in registers)
+template <int NS>
+__device__ __forceinline__ double spr_dot(const double *__restrict__ Prow, const double (&v)[NS], uint32_t mask, bool internal)
+{
+  if (internal)
+  {
+    double a = Prow[0] * v[0];
+#pragma unroll
+    for (int j = 1; j < NS; ++j) a = fma(Prow[j], v[j], a);
+    return a;
+  }
+  double a = (mask & 1u) ? Prow[0] : 0.0;
+#pragma unroll
+  for (int j = 1; j < NS; ++j)
+    if ((mask >> j) & 1u) a = a + Prow[j];
+  return a;
+}
+
+// NS states (a multiple of 4; 20 in practice), 4 categories on the blocked layout: thread per (pattern, category), lane
+// = category * 8 + pattern % 8 as above; the thread's NS-state vectors are NS/4 256-bit loads (a quarter-warp reads a
+// contiguous 256-byte block per load), both conditional vectors and the new node's vector stay in registers, the three
+// P-matrices of the block's candidate sit in shared memory with a 2-double pad per category (the 4 quarter-warps of a
+// broadcast load hit different banks).  Same arithmetic as k_spr_candidates.
+template <int NS>
+__global__ void __launch_bounds__(kSprThreads)
+    k_spr_candidates_reg4(const SprCandDev *__restrict__ cands, int blocks_per_cand, SideDev prune,
+                          const double *__restrict__ Pp, int link_on_left, const ModelDev *__restrict__ mod, int npat,
+                          const double *__restrict__ wght, const short *__restrict__ invar,
+                          const uint32_t *__restrict__ tipmask, int apply_scaling, double *__restrict__ partials,
+                          int *__restrict__ warn_out)
+{
+  constexpr int NCATG = 4, NN = NS * NS, PS = NN + 2, KB = NS / 4;
+  extern __shared__ double spr_sm[];  // [3][NCATG][PS] | pi[NS] | probs[NCATG]
+  double *sP = spr_sm, *sPi = spr_sm + 3 * NCATG * PS, *sProb = sPi + NS;
+  const int        cand = blockIdx.x / blocks_per_cand, blk = blockIdx.x % blocks_per_cand;
+  const SprCandDev cd = cands[cand];
+  for (int t = threadIdx.x; t < NCATG * NN; t += blockDim.x)
+  {
+    const int cc = t / NN, e = t % NN;
+    sP[(0 * NCATG + cc) * PS + e] = cd.Pa[t];
+    sP[(1 * NCATG + cc) * PS + e] = cd.Pb[t];
+    sP[(2 * NCATG + cc) * PS + e] = Pp[t];
+  }
+  if (threadIdx.x < NS) sPi[threadIdx.x] = mod->pi[threadIdx.x];
+  if (threadIdx.x < NCATG) sProb[threadIdx.x] = mod->probs[threadIdx.x];
+  __syncthreads();
+  const double   big = two_to_large(), small = inv_two_to_large();
+  const uint32_t full = (NS >= 32) ? 0xffffffffu : ((1u << NS) - 1u);
+  const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int      c = lane >> 3, r = lane & 7;
+  const int      n_groups = (npat + 7) >> 3;
+  double         acc = 0.0;
+  int            warn = 0;
+
+  for (int grp = blk * wpb + warp; grp < n_groups; grp += blocks_per_cand * wpb)
+  {
+    const int    site = grp * 8 + r;
+    const bool   in = site < npat;
+    const double w = in ? wght[site] : 0.0;
+    const bool   live = in && (w > DBL_MIN);
+    const size_t off = (((size_t)grp * NCATG + c) * KB * 8 + r) * 4;  // clv_off(site, c, 0): + kb * 32 per 4 states
+    double       x[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) x[i] = 0.0;
+    int      sx = 0;
+    uint32_t mp = 0u;
+    if (live)
+    {
+      double   v[NS];
+      bool     oa = true, ob = true;
+      uint32_t m = 0u;
+      // child a
+      if (cd.a.clv)
+      {
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb)
+        {
+          const double4a q = ld256(cd.a.clv + off + kb * 32);
+          v[kb * 4 + 0] = q.x, v[kb * 4 + 1] = q.y, v[kb * 4 + 2] = q.z, v[kb * 4 + 3] = q.w;
+          oa = oa && all_one(q);
+        }
+        sx += cd.a.scale[site];
+      }
+      else
+      {
+        m = tipmask[cd.a.tip[site]];
+        oa = (m == full);
+      }
+      {
+        const double *P = sP + (0 * NCATG + c) * PS;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) x[i] = spr_dot<NS>(P + i * NS, v, m, cd.a.clv != nullptr);
+      }
+      // child b
+      m = 0u;
+      if (cd.b.clv)
+      {
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb)
+        {
+          const double4a q = ld256(cd.b.clv + off + kb * 32);
+          v[kb * 4 + 0] = q.x, v[kb * 4 + 1] = q.y, v[kb * 4 + 2] = q.z, v[kb * 4 + 3] = q.w;
+          ob = ob && all_one(q);
+        }
+        sx += cd.b.scale[site];
+      }
+      else
+      {
+        m = tipmask[cd.b.tip[site]];
+        ob = (m == full);
+      }
+      {
+        const double *P = sP + (1 * NCATG + c) * PS;
+        const bool    ones = oa && ob;
+#pragma unroll
+        for (int i = 0; i < NS; ++i)
+        {
+          const double ub = spr_dot<NS>(P + i * NS, v, m, cd.b.clv != nullptr);
+          x[i] = ones ? 1.0 : x[i] * ub;
+        }
+      }
+      if (!prune.clv) mp = tipmask[prune.tip[site]];
+    }
+    double largest = x[0];
+#pragma unroll
+    for (int i = 1; i < NS; ++i) largest = fmax(largest, x[i]);
+    largest = fmax(largest, __shfl_xor_sync(0xffffffffu, largest, 8));
+    largest = fmax(largest, __shfl_xor_sync(0xffffffffu, largest, 16));
+    const bool rescale = (largest < small) && apply_scaling;
+    if (rescale)
+    {
+#pragma unroll
+      for (int i = 0; i < NS; ++i) x[i] *= big;
+      sx += kLarge;
+    }
+    double term = 0.0;
+    if (live)
+    {
+      double pv[NS];
+      if (prune.clv)
+      {
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb)
+        {
+          const double4a q = ld256(prune.clv + off + kb * 32);
+          pv[kb * 4 + 0] = q.x, pv[kb * 4 + 1] = q.y, pv[kb * 4 + 2] = q.z, pv[kb * 4 + 3] = q.w;
+        }
+      }
+      else
+      {
+#pragma unroll
+        for (int k = 0; k < NS; ++k) pv[k] = (double)((mp >> k) & 1u);
+      }
+      if (!link_on_left)
+      {  // the new node is the right-hand side: swap roles (L = pruned subtree, R = new node)
+#pragma unroll
+        for (int k = 0; k < NS; ++k)
+        {
+          const double tmp = x[k];
+          x[k] = pv[k];
+          pv[k] = tmp;
+        }
+      }
+      // from here: L = x, R = pv
+      const double *Pc = sP + (2 * NCATG + c) * PS;
+      const bool    unamb = link_on_left && !prune.clv && (__popc(mp) == 1);
+      double        lk;
+      if (unamb)
+      {  // avx.c:110-215
+        const int st = __ffs(mp) - 1;
+        double    q[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int b4 = 0; b4 < NS; b4 += 4)
+#pragma unroll
+          for (int t = 0; t < 4; ++t) q[t] = q[t] + Pc[st * NS + b4 + t] * x[b4 + t];
+        lk = sPi[st] * hsum4(q[0], q[1], q[2], q[3]);
+      }
+      else
+      {
+        lk = 0.0;
+#pragma unroll
+        for (int b4 = 0; b4 < NS; b4 += 4)
+        {
+          double y[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+          {
+            const int k = b4 + t;
+            double    a = 0.0;
+#pragma unroll
+            for (int l = 0; l < NS; ++l) a = fma(Pc[k * NS + l], x[l], a);
+            y[t] = a * (pv[k] * sPi[k]);
+          }
+          lk = lk + hsum4(y[0], y[1], y[2], y[3]);
+        }
+      }
+      term = lk * sProb[c];
+    }
+    const double t1 = __shfl_sync(0xffffffffu, term, r + 8);
+    const double t2 = __shfl_sync(0xffffffffu, term, r + 16);
+    const double t3 = __shfl_sync(0xffffffffu, term, r + 24);
+    if (live && c == 0)
+    {
+      double site_lk = 0.0 + term;
+      site_lk = site_lk + t1;
+      site_lk = site_lk + t2;
+      site_lk = site_lk + t3;
+      int fact = sx + (prune.scale ? prune.scale[site] : 0);
+      if (mod->invar_flag)
+      {
+        bool   ovf;
+        double inv = invariant_lk(fact, invar[site], mod->pi, &ovf);
+        if (ovf)
+        {
+          fact = 0;
+          inv = invariant_lk(0, invar[site], mod->pi, &ovf);
+          site_lk = inv * mod->pinv;
+        }
+        else
+          site_lk = site_lk * (1. - mod->pinv) + inv * mod->pinv;
+      }
+      if (site_lk < DBL_MIN)
+      {
+        site_lk = DBL_MIN;
+        warn = 1;
+      }
+      acc += w * (log(site_lk) - kLog2 * fact);
+    }
+  }
+
+  __shared__ double sred[kSprThreads / 32];
+  __shared__ int    swarn;
+  if (threadIdx.x == 0) swarn = 0;
+  __syncthreads();
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = acc;
+  if (warn) atomicOr(&swarn, 1);
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    double s = 0.0;
+    for (int wq = 0; wq < kSprThreads / 32; ++wq) s += sred[wq];
+    partials[(size_t)cand * blocks_per_cand + blk] = s;
+    if (swarn) atomicOr(&warn_out[cand], 1);
+  }
+}
+
 __global__ void k_spr_finish(const double *__restrict__ partials, int blocks_per_cand, int n_cand, double *__restrict__ lnl)
 {
   const int cand = blockIdx.x * blockDim.x + threadIdx.x;

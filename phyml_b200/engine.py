@@ -365,16 +365,25 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ batched SPR candidates
-    def spr_candidates(self, prune: Side, l_prune: float, link_on_left: bool, cands):
-        """Scores of many regraft positions of one pruned subtree in one call (``plk_spr_candidates``).
-        ``cands``: sequence of (Side a, l_a, Side b, l_b).  Returns (lnl array, warning flags)."""
+    @staticmethod
+    def pack_spr_cands(cands):
+        """Sequence of (Side a, l_a, Side b, l_b) -> C array of ``plk_spr_cand`` (reusable across calls)."""
         arr = (_SprCand * max(1, len(cands)))()
         for i, (a, la, b, lb) in enumerate(cands):
             arr[i] = _SprCand(_Side(a.tip, a.clv), float(la), _Side(b.tip, b.clv), float(lb))
-        lnl = np.zeros(len(cands))
-        warn = np.zeros(len(cands), dtype=np.int32)
+        arr._n = len(cands)
+        return arr
+
+    def spr_candidates(self, prune: Side, l_prune: float, link_on_left: bool, cands):
+        """Scores of many regraft positions of one pruned subtree in one call (``plk_spr_candidates``).
+        ``cands``: sequence of (Side a, l_a, Side b, l_b) or the result of ``pack_spr_cands``.
+        Returns (lnl array, warning flags)."""
+        arr = cands if hasattr(cands, "_n") else self.pack_spr_cands(cands)
+        n = arr._n
+        lnl = np.zeros(n)
+        warn = np.zeros(n, dtype=np.int32)
         self._ck(self.lib.plk_spr_candidates(self.h, _Side(prune.tip, prune.clv), float(l_prune), int(bool(link_on_left)),
-                                             len(cands), C.cast(arr, C.c_void_p), _ptr(lnl), _ptr(warn)))
+                                             n, C.cast(arr, C.c_void_p), _ptr(lnl), _ptr(warn)))
         return lnl, warn
 
     # ------------------------------------------------------------------ parsimony (src/pars.c)

