@@ -396,9 +396,96 @@ def run_b200(args):
                     sec[nm] = secondary_of(r2, peaks)
                 except Exception as ex:  # a secondary workload must never take the headline line down
                     sec[nm] = {"error": f"{type(ex).__name__}: {ex}"}
+            try:
+                sec["spr_path_dna_100x50k"] = spr_path_latency(local)
+            except Exception as ex:
+                sec["spr_path_dna_100x50k"] = {"error": f"{type(ex).__name__}: {ex}"}
             out["secondary"] = sec
     if rank == 0:
         print(json.dumps(out))
+
+
+def spr_path_latency(local, name="dna_100x50k"):
+    """The calls that bound an SPR search (BASELINE configs[4] shape, 100 taxa x 50 000 sites), through the C ABI:
+    one regraft candidate as the reference issues it (P-matrices + Update_Partial_Lk at the new node + Lk(b_arrow),
+    spr.c:589-650) against the same candidates scored in one call (plk_spr_candidates), one dLk, and Pars(NULL) with both
+    sides (pars.c:20) -- host wall-clock per call, results cross-checked between the two candidate paths."""
+    from phyml_b200.engine import Engine, pack_ops
+    from phyml_b200.lk import LkTree
+    from phyml_b200.tree import PartialOp, Side
+
+    w = wl.WORKLOADS[name]
+    m, _pin = wl.evaluation_model(name)
+    tree = wl.make_tree(w)
+    pat = wl.make_patterns(name, [0], procs=8)
+    eng = Engine(tree.n_otu, pat.n_pattern, m.ns, m.ncatg, tree.n_clv_handles + 1, tree.n_edges + 3, device=local)
+    t = LkTree(tree, pat, m, eng)
+    t.Set_Both_Sides(1)
+    t.Lk()
+
+    def timeit(fn, n, warm=5):
+        for _ in range(warm):
+            fn()
+        eng.sync()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        eng.sync()
+        return (time.perf_counter() - t0) / n * 1e6
+
+    tip = 3
+    te = tree.adj[tip][0][0]
+    prune, l_prune = tree.side_of(te, tip), float(tree.l[te])
+    cands = []
+    for e in range(tree.n_edges):
+        if e != te:
+            a, b = tree.edge_sides(e)
+            cands.append((a, 0.5 * tree.l[e], b, 0.5 * tree.l[e]))
+    packed = eng.pack_spr_cands(cands)
+    tmp, ha, hb, hp = tree.n_clv_handles, tree.n_edges, tree.n_edges + 1, tree.n_edges + 2
+    hs = np.array([ha, hb, hp], dtype=np.int32)
+
+    def one(c):
+        a, la, b, lb = c
+        eng.update_pmats(hs, np.array([la, lb, l_prune]))
+        eng.update_partials(pack_ops([PartialOp(dst=tmp, c1=a, pmat1=ha, c2=b, pmat2=hb)]))
+        return eng.edge_lnl(Side(clv=tmp), prune, hp)
+
+    seq = np.array([one(c) for c in cands])
+    got, _ = eng.spr_candidates(prune, l_prune, True, packed)
+    rel = float(np.max(np.abs(got - seq) / np.abs(seq)))
+    if rel > 1e-12:
+        raise RuntimeError(f"batched candidate scores differ from the call sequence: {rel:.3e}")
+    l0 = eng.launch_count
+    t_batch = timeit(lambda: eng.spr_candidates(prune, l_prune, True, packed), n=20)
+    launches_batch = (eng.launch_count - l0) // 25
+    t_seq = timeit(lambda: one(cands[7]), n=200)
+    e = tree.n_edges // 2
+    left, rght = tree.edge_sides(e)
+    eng.eigen_lr(left, rght)
+    t_dlk = timeit(lambda: eng.lnl_dlnl(0.05), n=200)
+    # parsimony: tips = the bit masks of the tip table, Pars(NULL) with both sides in one call
+    table = pat.table()
+    masks = (table.astype(np.int64) << np.arange(m.ns)[None, :]).sum(axis=1).astype(np.int32)
+    eng.pars_create(tree.n_clv_handles + 1)
+    zero = np.zeros(pat.n_pattern, dtype=np.int32)
+    for i in range(tree.n_otu):
+        eng.pars_set_buffer(tree.pars_tip_handle(i), ui=masks[pat.codes[i]], pars=zero)
+    a0, d0 = 0, tree.adj[0][0][1]
+    e0 = tree.adj[0][0][0]
+    pops = np.asarray(tree.pars_ops(tree.post_order_ops(a0, d0)) + tree.pars_ops(tree.pre_order_ops(a0, d0)), dtype=np.int32)
+    c_pars = eng.pars_traverse_edge(pops, 2 * e0, 2 * e0 + 1)
+    if c_pars != eng.pars_edge(2 * (tree.n_edges // 2), 2 * (tree.n_edges // 2) + 1):
+        raise RuntimeError("parsimony score depends on the edge it is summed at")
+    t_pars = timeit(lambda: eng.pars_traverse_edge(pops, 2 * e0, 2 * e0 + 1), n=100)
+    res = {"workload": w.desc, "patterns": pat.n_pattern, "unit": "us per call (host wall-clock through the C ABI)",
+           "candidate_as_the_reference_issues_it": round(t_seq, 2),
+           "candidate_batched": round(t_batch / len(cands), 2), "candidates_per_batch": len(cands),
+           "batch_launches": int(launches_batch), "batched_vs_sequence_rel_err": rel,
+           "dLk": round(t_dlk, 2), "pars_null_both_sides": round(t_pars, 2), "pars_updates": int(len(pops)),
+           "c_pars": int(c_pars)}
+    eng.close()
+    return res
 
 
 # ======================================================================================================
