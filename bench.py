@@ -332,6 +332,36 @@ def roofline_of(rec, peaks):
     return out
 
 
+def measured_traffic(name, timeout=240):
+    """DRAM bytes (read + write) of ONE launch of the traversal kernel, measured now: this same script re-run for one
+    step under `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` (warm launch: 3 skipped).  Only the byte counters
+    are taken from the profiled run -- never a time.  Returns (bytes, source) or (None, why)."""
+    import shutil
+
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None, "ncu not found"
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "--print-units", "base",
+           "-k", "regex:k_traverse", "-s", "3", "-c", "1", "--csv", sys.executable, os.path.abspath(__file__),
+           "--steps", "1", "--warmup", "3", "--no-cpu-baseline", "--no-secondary", "--no-traffic", "--workload", name]
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    except Exception as ex:  # noqa: BLE001
+        return None, f"ncu pass failed: {type(ex).__name__}"
+    tot, kern = 0.0, None
+    for ln in res.stdout.splitlines():
+        if "dram__bytes_" in ln and ln.startswith('"'):
+            f = [x.strip('"') for x in ln.split('","')]
+            try:
+                tot += float(f[-1].replace(",", ""))
+                kern = f[4].split("(")[0]
+            except (ValueError, IndexError):
+                pass
+    if tot <= 0.0:
+        return None, "ncu pass produced no dram counters"
+    return tot, f"measured in this run: ncu dram__bytes_read.sum + dram__bytes_write.sum of one warm launch of {kern}"
+
+
 def secondary_of(rec, peaks):
     rf = roofline_of(rec, peaks)
     return {"workload": rec["desc"], "name": rec["name"], "patterns": rec["P"], "n_taxa": rec["n_taxa"],
@@ -382,10 +412,18 @@ def run_b200(args):
             "clocks": rec["clocks"],
             "roofline": roofline_of(rec, peaks),
         }
+        if world == 1 and not args.no_traffic:
+            pass  # filled in below, after the process group / timing legs are done
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0 and world == 1:
+        if not args.no_traffic:
+            tr, src = measured_traffic(name)
+            if tr is not None:
+                out["roofline"]["traffic"], out["roofline"]["traffic_source"] = tr, src
+            else:
+                out["roofline"]["traffic_note"] = src + "; value from the committed capture instead"
         if not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(name, cores=1, sites=args.cpu_sites, evals=args.cpu_evals, gpu_check=local)
         if not args.no_secondary and name == "dna_100x100k":
@@ -601,6 +639,7 @@ def main():
                     help="default: dna_100x100k on 1 GPU (BASELINE configs[1]), dna_500x1M on N>1 (configs[3], strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-traffic", action="store_true", help="skip the in-run ncu pass that measures roofline.traffic")
     ap.add_argument("--cpu-sites", type=int, default=25_000)
     ap.add_argument("--cpu-evals", type=int, default=40)
     args = ap.parse_args()
