@@ -67,6 +67,7 @@
 #include "free.h"
 #include "alrt.h"
 #include "pars.h"
+#include "ancestral.h"
 
 #include "../include/phyml_b200.h"
 
@@ -221,6 +222,14 @@ static int map_get(slot_t *map, int cap, const void *key, int *counter, int limi
     map[i].val = (*counter)++;
   }
   return map[i].val;
+}
+/* look-up only: -1 when the device has never seen this buffer name */
+static int map_find(const slot_t *map, int cap, const void *key)
+{
+  uintptr_t h = ((uintptr_t)key >> 4) * 0x9E3779B97F4A7C15ULL;
+  int       i = (int)(h % (uintptr_t)cap);
+  while (map[i].key && map[i].key != key) i = (i + 1) % cap;
+  return map[i].key ? map[i].val : -1;
 }
 static int clv_handle(shim_t *sh, const phydbl *p) { return map_get(sh->clv_map, sh->map_cap, p, &sh->n_clv, sh->clv_cap, "CLV"); }
 static int pm_handle(shim_t *sh, const phydbl *p) { return map_get(sh->pm_map, sh->map_cap, p, &sh->n_pm, sh->pm_cap, "P-matrix"); }
@@ -874,4 +883,73 @@ int One_Pars_Step(t_edge *b, t_tree *tree)
   PhyML_Fprintf(stderr, "\n. phyml_b200: One_Pars_Step() reads host parsimony buffers that live on the device.\n");
   Exit("\n");
   return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Host readers of CLVs / scalers / P-matrices: Ancestral_Sequences       */
+/* (src/ancestral.c:527, called by main() after Lk(NULL) with both sides, main.c:289) reads            */
+/* b->p_lk_left / p_lk_rght, sum_scale_* and Pij_rr of every edge on the host.  While it runs, the     */
+/* address-only arena is backed by real pages and filled from the device; afterwards the pages are     */
+/* given back.  (The host memory this needs is the reference's own requirement for this analysis.)     */
+static void mirror_side(shim_t *sh, t_node *n, phydbl *p_lk, int *sum_scale)
+{
+  int h;
+  if (!n || n->tax || !p_lk) return; /* tips keep their host p_lk_tip_r (make.c:687-705) */
+  h = map_find(sh->clv_map, sh->map_cap, p_lk);
+  if (h < 0) return;                 /* never computed on the device: the reference would read zeros as well */
+  CK(plk_get_clv(sh->inst, h, p_lk, sum_scale), sh);
+}
+
+static void mirror_edge(shim_t *sh, t_edge *b)
+{
+  const int ns = sh->tree->mod->ns, nc = sh->tree->mod->ras->n_catg;
+  int       h, c, i, j;
+  if (!b) return;
+  mirror_side(sh, b->left, b->p_lk_left, b->sum_scale_left);
+  mirror_side(sh, b->rght, b->p_lk_rght, b->sum_scale_rght);
+  if (b->Pij_rr && (h = map_find(sh->pm_map, sh->map_cap, b->Pij_rr)) >= 0)
+  {
+    CK(plk_get_pmat(sh->inst, h, b->Pij_rr), sh);
+    if (b->tPij_rr)
+      for (c = 0; c < nc; ++c)
+        for (i = 0; i < ns; ++i)
+          for (j = 0; j < ns; ++j) b->tPij_rr[c * ns * ns + j * ns + i] = b->Pij_rr[c * ns * ns + i * ns + j]; /* models.c:313 */
+  }
+}
+
+static void host_mirror_begin(shim_t *sh)
+{
+  t_tree *tree = sh->tree;
+  int     e;
+  flush(sh);
+  if (sh->arena && mprotect(sh->arena, sh->arena_bytes, PROT_READ | PROT_WRITE) != 0)
+  {
+    PhyML_Fprintf(stderr, "\n. phyml_b200: cannot back the likelihood arena with host memory (%.1f MB)\n", (double)sh->arena_bytes / 1e6);
+    Exit("\n");
+  }
+  for (e = 0; e < 2 * tree->n_otu - 3; ++e) mirror_edge(sh, tree->a_edges[e]);
+  if (tree->n_root)
+  {
+    mirror_edge(sh, tree->n_root->b[1]);
+    mirror_edge(sh, tree->n_root->b[2]);
+  }
+}
+
+static void host_mirror_end(shim_t *sh)
+{
+  if (!sh->arena) return;
+  madvise(sh->arena, sh->arena_bytes, MADV_DONTNEED);
+  mprotect(sh->arena, sh->arena_bytes, PROT_NONE);
+}
+
+/* src/ancestral.c:527-604 */
+void Ancestral_Sequences(t_tree *tree, int print)
+{
+  static void (*orig)(t_tree *, int) = NULL;
+  shim_t *sh = shim_of(tree);
+  if (!orig) orig = (void (*)(t_tree *, int))dlsym(RTLD_NEXT, "Ancestral_Sequences");
+  if (!sh) no_instance("Ancestral_Sequences");
+  host_mirror_begin(sh);
+  orig(tree, print);
+  host_mirror_end(sh);
 }

@@ -128,6 +128,51 @@ def test_rooted_tree(tmp_path):
         assert abs(x - y) <= 1e-11 * abs(y), (x, y)
 
 
+def _numeric_rows(path):
+    """every line of a PhyML text output as a list of tokens, numbers converted to float"""
+    rows = []
+    for ln in open(path).read().splitlines():
+        toks = []
+        for t in ln.split():
+            try:
+                toks.append(float(t))
+            except ValueError:
+                toks.append(t)
+        if toks:
+            rows.append(toks)
+    return rows
+
+
+@needs_bins
+def test_host_readers_ancestral_sequences_and_site_likelihoods(tmp_path):
+    """--ancestral: Ancestral_Sequences (ancestral.c:527) reads every edge's CLVs, scalers and P-matrices on the HOST;
+    --print_site_lnl: Print_Site_Lk (io.c:1870) reads cur_site_lk / unscaled_site_lk_cat / fact_sum_scale.  The binding
+    backs the address-only arena with pages filled from the device while the reader runs, and mirrors the per-site arrays
+    after Lk(NULL).  Both output files must equal the CPU run's."""
+    phy, nwk = stage(tmp_path, "synth_dna_deep")
+    lines = open(os.path.join(str(tmp_path), phy)).read().splitlines()
+    n_sites = lines[0].split()[1]
+    for name in ("a.phy", "b.phy"):
+        with open(os.path.join(str(tmp_path), name), "w") as f:
+            f.write(f"16 {n_sites}\n" + "\n".join(lines[1:17]) + "\n")
+    args = ["-d", "nt", "-m", "HKY85", "-c", "4", "-a", "0.5", "-f", "e", "-o", "lr", "-b", "0", "--r_seed", "1",
+            "--no_memory_check", "--ancestral", "--print_site_lnl"]
+    a, _ = run(B200, str(tmp_path), ["-i", "a.phy"] + args)
+    b, _ = run(REF, str(tmp_path), ["-i", "b.phy"] + args)
+    assert abs(a - b) <= 1e-6 * abs(b), (a, b)
+    for suffix, min_rows in (("_phyml_ancestral_seq.txt", 1000), ("_phyml_lk.txt", 100)):
+        ra = _numeric_rows(os.path.join(str(tmp_path), "a.phy" + suffix))
+        rb = _numeric_rows(os.path.join(str(tmp_path), "b.phy" + suffix))
+        assert len(ra) == len(rb) >= min_rows, (suffix, len(ra), len(rb))
+        for x, y in zip(ra, rb):
+            assert len(x) == len(y), (x, y)
+            for u, v in zip(x, y):
+                if isinstance(v, float) and isinstance(u, float):
+                    assert abs(u - v) <= 2e-4 * max(abs(v), 1e-6) + 1e-12, (suffix, x, y)
+                elif "phy" not in str(v):   # file names differ (a.phy / b.phy)
+                    assert u == v, (suffix, x, y)
+
+
 def _topology(tmp, phy):
     """Newick of the tree PhyML wrote next to the alignment with branch lengths and supports removed."""
     txt = open(os.path.join(tmp, phy + "_phyml_tree.txt")).read().strip()
