@@ -150,6 +150,13 @@ int plk_lk_full(plk_instance *inst, int n_pmat, const int *pmat, const double *l
                 const plk_op *ops, plk_side left, plk_side rght, int edge_pmat, double *lnl,
                 int *numerical_warning);
 
+/* plk_lk_full split in two for hosts that pipeline evaluations: _begin enqueues everything and returns, _wait returns
+ * the result.  Between the two only uploads (plk_set_*) may be issued: they are ordered behind the evaluation on the
+ * device, and the host-to-device copy of plk_set_all_tip_codes_packed4 overlaps it (own copy stream). */
+int plk_lk_full_begin(plk_instance *inst, int n_pmat, const int *pmat, const double *lengths, int n_ops,
+                      const plk_op *ops, plk_side left, plk_side rght, int edge_pmat);
+int plk_lk_wait(plk_instance *inst, double *lnl, int *numerical_warning);
+
 /* ---- K3: eigen-basis projection -------------------------------------------------------------
  * replaces Update_Eigen_Lr (src/lk.c:1038-1114, src/avx.c:21-105): tree->dot_prod stays on the
  * device; also latches fact_sum_scale = scale(left)+scale(rght) for K4. */

@@ -161,6 +161,11 @@ struct plk_instance
   bool                pars_site_valid = false;
   bool                wght_integral = true;  // every pattern weight is an integer (plk_set_pattern_weights)
 
+  // host-to-device copies of the tip codes run on their own stream so that they overlap compute that was enqueued
+  // earlier (plk_lk_full_begin ... upload of the next inputs ... plk_lk_wait)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t  ev_copy = nullptr, ev_unpack = nullptr;
+
   // batched SPR candidates (plk_spr_candidates): scratch P-matrices, per-block partial sums, results
   double *d_spr_pmat = nullptr, *d_spr_partials = nullptr, *d_spr_lnl = nullptr;
   int    *d_spr_warn = nullptr;
@@ -576,6 +581,9 @@ void plk_destroy(plk_instance *inst)
     if (inst->h_stage[s]) cudaFreeHost(inst->h_stage[s]);
     if (inst->stage_ev[s]) cudaEventDestroy(inst->stage_ev[s]);
   }
+  if (inst->copy_stream) cudaStreamDestroy(inst->copy_stream);
+  if (inst->ev_copy) cudaEventDestroy(inst->ev_copy);
+  if (inst->ev_unpack) cudaEventDestroy(inst->ev_unpack);
   if (inst->stream) cudaStreamDestroy(inst->stream);
   delete inst;
 }
@@ -703,16 +711,27 @@ int plk_set_all_tip_codes_packed4(plk_instance *inst, const uint8_t *packed, siz
   {
     int rc = dev_alloc(inst, &inst->d_tippacked, pstride * inst->cfg.n_tips);
     if (rc) return rc;
+    CU_TRY(inst, cudaStreamCreateWithFlags(&inst->copy_stream, cudaStreamNonBlocking));
+    CU_TRY(inst, cudaEventCreateWithFlags(&inst->ev_copy, cudaEventDisableTiming));
+    CU_TRY(inst, cudaEventCreateWithFlags(&inst->ev_unpack, cudaEventDisableTiming));
     CU_TRY(inst, cudaMemsetAsync(inst->d_tippacked, 0, pstride * inst->cfg.n_tips, inst->stream));
+    CU_TRY(inst, cudaEventRecord(inst->ev_unpack, inst->stream));
   }
+  // the copy only has to wait for the previous unpack (the last reader of the staging buffer), not for the compute
+  // enqueued since: it overlaps a traversal that is still running; the unpack that follows is ordered on the
+  // instance's stream as before, so every later call sees the new codes
+  CU_TRY(inst, cudaStreamWaitEvent(inst->copy_stream, inst->ev_unpack, 0));
   CU_TRY(inst, cudaMemcpy2DAsync(inst->d_tippacked, pstride, packed, host_stride, row, inst->cfg.n_tips,
-                                 cudaMemcpyHostToDevice, inst->stream));
+                                 cudaMemcpyHostToDevice, inst->copy_stream));
+  CU_TRY(inst, cudaEventRecord(inst->ev_copy, inst->copy_stream));
+  CU_TRY(inst, cudaStreamWaitEvent(inst->stream, inst->ev_copy, 0));
   const size_t n = pstride * inst->cfg.n_tips;
   const int    mode = inst->fused_dna ? 1 : (inst->fused_aa ? 2 : 0);
   k_unpack_codes4<<<(unsigned)std::min<size_t>((n / 8 + 255) / 256 + 1, 8192), 256, 0, inst->stream>>>(
       inst->d_tippacked, inst->d_tipcodes, mode ? inst->d_tiprows : nullptr, n, inst->d_tipmask, mode);
   inst->launches++;
   CU_TRY(inst, cudaGetLastError());
+  CU_TRY(inst, cudaEventRecord(inst->ev_unpack, inst->stream));
   inst->tiprows_dirty = false;
   return PLK_OK;
 }
@@ -1607,6 +1626,30 @@ int plk_lk_full(plk_instance *inst, int n_pmat, const int *pmat, const double *l
   const int rc = plk_update_pmats(inst, n_pmat, pmat, l);
   if (rc) return rc;
   return plk_traverse_edge_lnl(inst, n_ops, ops, left, rght, edge_pmat, lnl, warn);
+}
+
+// the same evaluation split in two: everything is enqueued by _begin, the result is awaited by _wait; uploads of the
+// NEXT evaluation's inputs may be issued in between (they are ordered behind this evaluation on the device, and the
+// tip-code copy itself overlaps it)
+int plk_lk_full_begin(plk_instance *inst, int n_pmat, const int *pmat, const double *l, int n_ops, const plk_op *ops,
+                      plk_side left, plk_side rght, int edge_pmat)
+{
+  ARG_CHECK(inst, n_ops >= 0 && (n_ops == 0 || ops), "plk_lk_full_begin: bad arguments");
+  const int rc = plk_update_pmats(inst, n_pmat, pmat, l);
+  if (rc) return rc;
+  if (!inst->shards.empty())
+  {
+    FOR_SHARDS(inst, traverse_edge_launch(sh, n_ops, ops, left, rght, edge_pmat));
+    return PLK_OK;
+  }
+  return traverse_edge_launch(inst, n_ops, ops, left, rght, edge_pmat);
+}
+
+int plk_lk_wait(plk_instance *inst, double *lnl, int *warn)
+{
+  ARG_CHECK(inst, lnl != nullptr, "plk_lk_wait: bad arguments");
+  if (!inst->shards.empty()) return finish_sharded(inst, lnl, nullptr, warn);
+  return finish_reduction(inst, lnl, nullptr, warn);
 }
 
 // ---- K3 ------------------------------------------------------------------------------------------

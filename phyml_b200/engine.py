@@ -52,7 +52,7 @@ EXPORTS = [
     "plk_comm_p2p_export", "plk_comm_p2p_init", "plk_create_sharded", "plk_n_shards",
     "plk_launch_count", "plk_device_bytes", "plk_stream", "plk_version",
     "plk_pars_create", "plk_pars_set_buffer", "plk_pars_get_buffer", "plk_pars_update", "plk_pars_edge",
-    "plk_pars_traverse_edge", "plk_get_site_pars", "plk_spr_candidates",
+    "plk_pars_traverse_edge", "plk_get_site_pars", "plk_spr_candidates", "plk_lk_full_begin", "plk_lk_wait",
 ]
 
 _lib = None
@@ -91,6 +91,8 @@ def load_library() -> C.CDLL:
     lib.plk_edge_lnl.argtypes = [vp, _Side, _Side, C.c_int, dp, ip]
     lib.plk_traverse_edge_lnl.argtypes = [vp, C.c_int, vp, _Side, _Side, C.c_int, dp, ip]
     lib.plk_lk_full.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, _Side, _Side, C.c_int, dp, ip]
+    lib.plk_lk_full_begin.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, _Side, _Side, C.c_int]
+    lib.plk_lk_wait.argtypes = [vp, dp, ip]
     lib.plk_eigen_lr.argtypes = [vp, _Side, _Side]
     lib.plk_edge_lnl_dlnl.argtypes = [vp, dp, dp, dp, ip]
     lib.plk_edge_lnl_eigen.argtypes = [vp, C.c_double, dp, ip]
@@ -320,6 +322,26 @@ class Engine:
             return out.value
 
         return call
+
+    def lk_full_begin_call(self, handles, lengths, ops, left: Side, rght: Side, pmat: int):
+        """``plk_lk_full_begin`` with bound arguments (see ``lk_full_call``): enqueues one full-tree evaluation and
+        returns; ``lk_wait()`` returns its lnL.  Uploads of the next inputs may be issued in between."""
+        h = np.ascontiguousarray(handles, dtype=np.int32)
+        l = np.ascontiguousarray(lengths, dtype=np.float64)
+        arr = ops if isinstance(ops, np.ndarray) else pack_ops(ops)
+        args = (self.h, len(h), _ptr(h), _ptr(l), len(arr), _ptr(arr), _Side(left.tip, left.clv), _Side(rght.tip, rght.clv), pmat)
+        fn, ck = self.lib.plk_lk_full_begin, self._ck
+
+        def call(_keep=(h, l, arr)):
+            ck(fn(*args))
+
+        return call
+
+    def lk_wait(self) -> float:
+        out, warn = C.c_double(0.0), C.c_int(0)
+        self._ck(self.lib.plk_lk_wait(self.h, C.byref(out), C.byref(warn)))
+        self.numerical_warning = warn.value
+        return out.value
 
     # ------------------------------------------------------------------ K3 / K4
     def eigen_lr(self, left: Side, rght: Side):

@@ -318,3 +318,43 @@ def test_packed_tip_codes_upload():
     a.Lk()
     b.Lk()
     assert a.Lk(0) == b.Lk(0)
+
+
+def test_lk_full_begin_wait_with_the_next_upload_in_between():
+    """plk_lk_full_begin / plk_lk_wait: the tip codes of the NEXT evaluation are uploaded (own copy stream) while the
+    current one is in flight; neither evaluation may see the other's data."""
+    import torch
+
+    from phyml_b200.engine import pack_codes4, pack_ops
+
+    tree, m, pat = _synthetic(4, 40, 60000, seed=31, ambiguity=0.0)
+    rng = np.random.default_rng(5)
+    codes_a = pat.codes
+    codes_b = np.ascontiguousarray(codes_a[rng.permutation(tree.n_otu)])   # same patterns, taxa shuffled: another lnL
+    args = (tree.n_otu, pat.n_pattern, 4, 4, tree.n_clv_handles, tree.n_edges)
+    eng = Engine(*args)
+    eng.set_tip_table(pat.table())
+    eng.set_weights(pat.wght, pat.invar)
+    eng.set_model(m)
+    edges = np.arange(tree.n_edges, dtype=np.int32)
+    ops = pack_ops(tree.post_order_ops())
+    left, rght = tree.edge_sides(tree.root_edge)
+    full = eng.lk_full_call(edges, tree.l, ops, left, rght, tree.root_edge)
+    begin = eng.lk_full_begin_call(edges, tree.l, ops, left, rght, tree.root_edge)
+    pa = torch.from_numpy(pack_codes4(codes_a)).pin_memory()
+    pb = torch.from_numpy(pack_codes4(codes_b)).pin_memory()
+    eng.set_all_tip_codes_packed4(pa)
+    ref_a = full()
+    eng.set_all_tip_codes_packed4(pb)
+    ref_b = full()
+    assert ref_a != ref_b
+    for _ in range(5):
+        eng.set_all_tip_codes_packed4(pa)
+        begin()                               # evaluation of A in flight ...
+        eng.set_all_tip_codes_packed4(pb)     # ... while B is copied
+        assert eng.lk_wait() == ref_a
+        begin()
+        eng.set_all_tip_codes_packed4(pa)
+        assert eng.lk_wait() == ref_b
+        begin()
+        assert eng.lk_wait() == ref_a
