@@ -123,3 +123,45 @@ def test_single_process_sharded_instance_two_devices():
     assert np.array_equal(ca, cb) and np.array_equal(sa, sb)
     s1, s2 = one.eng.get_site_lnl(), two.eng.get_site_lnl()
     np.testing.assert_allclose(s1["site_lnl"], s2["site_lnl"], rtol=1e-13)
+
+
+def test_single_process_sharded_parsimony_and_spr_candidates_two_devices():
+    """the round-2 entry points on a one-process, two-device instance: parsimony totals travel through the same
+    in-kernel exchange as lnL (exact integers), fractional weights through the serial chain in shard order, batched SPR
+    candidate scores are all-shard sums."""
+    import numpy as np
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import pars_checks as pk
+    from oracle_backend import OracleBackend
+    from phyml_b200.engine import Engine
+    from phyml_b200.lk import LkTree
+
+    c, g = pk.load("proteic_lg")
+    for general in (False, True):
+        eng = Engine(c.n_otu, c.P, c.ns, c.ncatg, c.tree.n_clv_handles, c.tree.n_edges, devices=[0, 1])
+        pk.check_full(c, g, eng, general, True)
+    tr, ui, w, step = pk.random_case(14, 4099, 4, seed=8, frac_weights=True)
+    args = (tr.n_otu, 4099, 4, 1, tr.n_clv_handles, tr.n_edges)
+    a = pk.run_random(tr, ui, w, step, Engine(*args, devices=[0, 1]), False)
+    b = pk.run_random(tr, ui, w, step, OracleBackend(*args), False)
+    assert a[0] == b[0] and (a[1] == b[1]).all() and a[2] == b[2]
+
+    tree, m, pat = _case()
+    args = (tree.n_otu, pat.n_pattern, 4, 4, tree.n_clv_handles, tree.n_edges)
+    one = LkTree(tree, pat, m, Engine(*args))
+    two = LkTree(tree, pat, m, Engine(*args, devices=[0, 1]))
+    for t in (one, two):
+        t.Set_Both_Sides(1)
+        t.Lk()
+    te = tree.adj[3][0][0]
+    cands = []
+    for e in range(tree.n_edges):
+        if e != te:
+            x, y = tree.edge_sides(e)
+            cands.append((x, 0.5 * tree.l[e], y, 0.5 * tree.l[e]))
+    r1, _ = one.eng.spr_candidates(tree.side_of(te, 3), float(tree.l[te]), True, cands)
+    r2, _ = two.eng.spr_candidates(tree.side_of(te, 3), float(tree.l[te]), True, cands)
+    assert (np.abs(r1 - r2) <= 1e-12 * np.abs(r1)).all()
