@@ -324,10 +324,23 @@ SideDev side_dev(plk_instance *inst, const plk_side &s)
   return d;
 }
 
+// blocks per SM of the reduction kernels (K2 / K4).  Every block ends with a fence + ticket atomic + barrier, and the
+// last block adds one partial per block: on the latency path (one Lk(b) / dLk per host round trip) fewer, longer
+// blocks finish sooner than one block per 128 work items.  PLK_REDUCE_BLOCKS_PER_SM overrides it for A/B runs.
+int reduce_blocks_per_sm()
+{
+  static const int v = [] {
+    const char *e = getenv("PLK_REDUCE_BLOCKS_PER_SM");
+    const int   k = e ? atoi(e) : 16;
+    return k < 1 ? 1 : (k > 16 ? 16 : k);
+  }();
+  return v;
+}
+
 int reduce_grid(const plk_instance *inst, int threads)
 {
   const int need = (inst->cfg.n_patterns + threads - 1) / threads;
-  return std::max(1, std::min(need, std::min(kMaxReduceBlocks, inst->num_sms * 16)));
+  return std::max(1, std::min(need, std::min(kMaxReduceBlocks, inst->num_sms * reduce_blocks_per_sm())));
 }
 
 // where the reduction kernel about to be launched delivers its result
@@ -831,6 +844,23 @@ int plk_update_pmats(plk_instance *inst, int n, const int *pmat, const double *l
   const int    per_slot = (int)(kStageBytes / sizeof(PmatJob));
   const int    threads = ((ns * ns + 31) / 32) * 32;
   const size_t smem = (size_t)(kMaxNs + ns * ns) * sizeof(double);
+  if (n > 0 && n <= kPmatInlineSmall)
+  {  // latency path (one candidate / one edge): small parameter block
+    PmatJobsInlineSmall jobs;
+    jobs.base = inst->d_pmat;
+    jobs.stride = (unsigned)inst->pmat_stride;
+    for (int i = 0; i < n; ++i)
+    {
+      ARG_CHECK(inst, pmat[i] >= 0 && pmat[i] < inst->cfg.n_pmat, "pmat handle out of range");
+      jobs.h[i] = pmat[i];
+      jobs.l[i] = l[i];
+    }
+    for (int i = n; i < kPmatInlineSmall; ++i) jobs.h[i] = 0, jobs.l[i] = 0.0;
+    k_pmat_inline_small<<<n * nc, threads, smem, inst->stream>>>(jobs, inst->d_model, ns, nc, ns == 4 ? 1 : (ns == 20 ? 2 : 0));
+    inst->launches++;
+    CU_TRY(inst, cudaGetLastError());
+    return PLK_OK;
+  }
   if (n <= kPmatInline)
   {  // job list in the kernel's parameter block: one launch, nothing staged
     static thread_local PmatJobsInline jobs;
@@ -1543,7 +1573,7 @@ static int edge_lnl_launch(plk_instance *inst, plk_side left, plk_side rght, int
   if (inst->fused_dna && inst->cfg.ncatg == 4)
   {  // coalesced 4-state kernel on the blocked layout: thread per (site, category)
     const int groups = (inst->cfg.n_patterns + 7) / 8;
-    const int grid = std::max(1, std::min((groups + 3) / 4, std::min(kMaxReduceBlocks, inst->num_sms * 16)));
+    const int grid = std::max(1, std::min((groups + 3) / 4, std::min(kMaxReduceBlocks, inst->num_sms * reduce_blocks_per_sm())));
     k_edge_lnl_dna<4><<<grid, 128, 0, inst->stream>>>(make_edge_dev(inst, left, rght, pmat));
   }
   else
@@ -1700,7 +1730,7 @@ static int k4_launch(plk_instance *inst, double l, int deriv)
   if (inst->cfg.ns == 4 && inst->cfg.ncatg == 4)
   {
     const int groups = (inst->cfg.n_patterns + 7) / 8;
-    const int grid = std::max(1, std::min((groups + 3) / 4, std::min(kMaxReduceBlocks, inst->num_sms * 16)));
+    const int grid = std::max(1, std::min((groups + 3) / 4, std::min(kMaxReduceBlocks, inst->num_sms * reduce_blocks_per_sm())));
     k_lnl_dlnl_dna<4><<<grid, 128, 0, inst->stream>>>(inst->d_dot_prod, inst->d_fact, inst->d_model, l, deriv,
                                                       inst->cfg.n_patterns, inst->d_wght, inst->d_invar,
                                                       inst->d_site_lnl, make_reduce_out(inst));

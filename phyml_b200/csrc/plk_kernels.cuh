@@ -297,6 +297,22 @@ __global__ void k_pmat_inline(const __grid_constant__ PmatJobsInline jobs, const
   pmat_body(jobs.base + (size_t)jobs.h[job] * jobs.stride, jobs.l[job], mod, ns, ncatg, with_tip_table);
 }
 
+// the same for a handful of matrices (one SPR candidate / one Lk(b): 1 to 3): a 112-byte parameter block instead of 12 KB
+constexpr int kPmatInlineSmall = 8;
+struct PmatJobsInlineSmall
+{
+  double  *base;
+  unsigned stride;
+  int      h[kPmatInlineSmall];
+  double   l[kPmatInlineSmall];
+};
+__global__ void k_pmat_inline_small(const __grid_constant__ PmatJobsInlineSmall jobs, const ModelDev *__restrict__ mod,
+                                    int ns, int ncatg, int with_tip_table)
+{
+  const int job = blockIdx.x / ncatg;
+  pmat_body(jobs.base + (size_t)jobs.h[job] * jobs.stride, jobs.l[job], mod, ns, ncatg, with_tip_table);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1, 4 states.  Thread <-> (site, category): its 4 states are one 32-byte vector, so consecutive
 // threads stream consecutive 32-byte words of each CLV (256-bit LDG/STG, fully coalesced).
