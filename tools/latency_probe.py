@@ -47,6 +47,8 @@ res["edge_lnl (Lk(b) without PMat)"] = timeit(lambda: eng.edge_lnl(left, rght, e
 res["update_pmat + edge_lnl (Lk(b))"] = timeit(lambda: (eng.update_pmats(E, L), eng.edge_lnl(left, rght, e)))
 res["1 update_partial + pmat + edge_lnl (one SPR candidate)"] = timeit(
     lambda: (eng.update_pmats(E, L), eng.update_partials(op), eng.edge_lnl(left, rght, e)))
+res["pmat + fused (1 update + edge_lnl) (one SPR candidate as the binding issues it: 2 launches)"] = timeit(
+    lambda: (eng.update_pmats(E, L), eng.traverse_edge_lnl(op, left, rght, e)))
 eng.eigen_lr(left, rght)
 res["eigen_lr (Update_Eigen_Lr)"] = timeit(lambda: eng.eigen_lr(left, rght))
 res["lnl_dlnl (one dLk)"] = timeit(lambda: eng.lnl_dlnl(0.05))
