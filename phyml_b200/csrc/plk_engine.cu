@@ -331,7 +331,7 @@ int reduce_blocks_per_sm()
 {
   static const int v = [] {
     const char *e = getenv("PLK_REDUCE_BLOCKS_PER_SM");
-    const int   k = e ? atoi(e) : 16;
+    const int   k = e ? atoi(e) : 4;
     return k < 1 ? 1 : (k > 16 ? 16 : k);
   }();
   return v;
