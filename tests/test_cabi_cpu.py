@@ -37,6 +37,27 @@ def test_struct_layouts_match_the_header():
     assert C.sizeof(engine._Side) == 8                # plk_side: {int tip; int clv;}
     assert C.sizeof(engine._Op) == 28                 # plk_op: dst, c1, pmat1, c2, pmat2
     assert engine.OP_DTYPE.itemsize == 28
+    assert C.sizeof(engine._SprCand) == 32            # plk_spr_cand: {plk_side a; double l_a; plk_side b; double l_b;}
+    import numpy as np
+    assert engine.Engine._pars_ops([(1, 2, 3)]).dtype == np.int32 and engine.Engine._pars_ops([(1, 2, 3)]).nbytes == 12  # plk_pars_op
+
+
+def test_shim_defines_every_re_bound_symbol():
+    """integration/lk_b200_shim.c must define, with external linkage, every reference entry point INTEGRATION.md lists."""
+    import subprocess
+
+    obj = os.path.join(ROOT, "integration", "_build", "lk_b200_shim.o")
+    if not os.path.exists(obj):
+        pytest.skip("shim not built (needs /root/reference at build time)")
+    out = subprocess.run(["nm", "--defined-only", obj], capture_output=True, text=True, check=True).stdout
+    defined = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    for sym in ("Lk", "dLk", "Update_Partial_Lk", "Update_PMat_At_Given_Edge", "Update_Eigen_Lr", "Make_Tree_For_Lk",
+                "Free_Tree_Lk", "Make_Edge_Lk", "posix_memalign", "aLRT", "Pars", "Pars_At_Given_Edge", "Update_Partial_Pars",
+                "Make_Tree_For_Pars", "Free_Tree_Pars", "Ancestral_Sequences"):
+        assert sym in defined, sym
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for sym in ("Update_Partial_Pars", "Pars_At_Given_Edge", "Ancestral_Sequences", "Make_Edge_Lk", "plk_spr_candidates"):
+        assert sym in text, sym
 
 
 def test_no_cpu_fallback():
