@@ -337,6 +337,22 @@ int reduce_blocks_per_sm()
   return v;
 }
 
+// threads per block of the two 4-state reduction kernels (thread per (pattern, category): a warp covers 8 patterns)
+int reduce_threads_dna()
+{
+  static const int v = [] {
+    const char *e = getenv("PLK_REDUCE_THREADS");
+    const int   k = e ? atoi(e) : 128;
+    return (k == 256 || k == 512) ? k : 128;
+  }();
+  return v;
+}
+int reduce_grid_dna(const plk_instance *inst)
+{
+  const int groups = (inst->cfg.n_patterns + 7) / 8, wpb = reduce_threads_dna() / 32;
+  return std::max(1, std::min((groups + wpb - 1) / wpb, std::min(kMaxReduceBlocks, inst->num_sms * reduce_blocks_per_sm())));
+}
+
 int reduce_grid(const plk_instance *inst, int threads)
 {
   const int need = (inst->cfg.n_patterns + threads - 1) / threads;
@@ -1572,9 +1588,7 @@ static int edge_lnl_launch(plk_instance *inst, plk_side left, plk_side rght, int
   ARG_CHECK(inst, pmat >= 0 && pmat < inst->cfg.n_pmat, "plk_edge_lnl: bad arguments");
   if (inst->fused_dna && inst->cfg.ncatg == 4)
   {  // coalesced 4-state kernel on the blocked layout: thread per (site, category)
-    const int groups = (inst->cfg.n_patterns + 7) / 8;
-    const int grid = std::max(1, std::min((groups + 3) / 4, std::min(kMaxReduceBlocks, inst->num_sms * reduce_blocks_per_sm())));
-    k_edge_lnl_dna<4><<<grid, 128, 0, inst->stream>>>(make_edge_dev(inst, left, rght, pmat));
+    k_edge_lnl_dna<4><<<reduce_grid_dna(inst), reduce_threads_dna(), 0, inst->stream>>>(make_edge_dev(inst, left, rght, pmat));
   }
   else
   {
@@ -1729,9 +1743,7 @@ static int k4_launch(plk_instance *inst, double l, int deriv)
   }
   if (inst->cfg.ns == 4 && inst->cfg.ncatg == 4)
   {
-    const int groups = (inst->cfg.n_patterns + 7) / 8;
-    const int grid = std::max(1, std::min((groups + 3) / 4, std::min(kMaxReduceBlocks, inst->num_sms * reduce_blocks_per_sm())));
-    k_lnl_dlnl_dna<4><<<grid, 128, 0, inst->stream>>>(inst->d_dot_prod, inst->d_fact, inst->d_model, l, deriv,
+    k_lnl_dlnl_dna<4><<<reduce_grid_dna(inst), reduce_threads_dna(), 0, inst->stream>>>(inst->d_dot_prod, inst->d_fact, inst->d_model, l, deriv,
                                                       inst->cfg.n_patterns, inst->d_wght, inst->d_invar,
                                                       inst->d_site_lnl, make_reduce_out(inst));
   }

@@ -2958,7 +2958,7 @@ __device__ __forceinline__ void edge_lnl_dna_group(const EdgeDev &e, const EdgeL
 }
 
 template <int NCATG>
-__global__ void __launch_bounds__(128) k_edge_lnl_dna(const __grid_constant__ EdgeDev e)
+__global__ void __launch_bounds__(512) k_edge_lnl_dna(const __grid_constant__ EdgeDev e)
 {
   constexpr int        SW = 32 / NCATG;
   const int            lane = threadIdx.x & 31;
@@ -3415,7 +3415,7 @@ __global__ void __launch_bounds__((W + 1) * 32, 1)
 
 // K4, 4 states: thread per (site, category); dot_prod is [site][catg][4] (plain layout).
 template <int NCATG>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(512)
     k_lnl_dlnl_dna(const double *__restrict__ dot_prod, const int *__restrict__ fact_sum_scale,
                    const ModelDev *__restrict__ mod, double l, int with_derivative, int npat,
                    const double *__restrict__ wght, const short *__restrict__ invar, double *__restrict__ site_lnl,
