@@ -326,12 +326,14 @@ SideDev side_dev(plk_instance *inst, const plk_side &s)
 
 // blocks per SM of the reduction kernels (K2 / K4).  Every block ends with a fence + ticket atomic + barrier, and the
 // last block adds one partial per block: on the latency path (one Lk(b) / dLk per host round trip) fewer, longer
-// blocks finish sooner than one block per 128 work items.  PLK_REDUCE_BLOCKS_PER_SM overrides it for A/B runs.
+// blocks finish sooner than one block per 128 work items.  Measured at 100 taxa x 50 000 sites (profiles/latency_r2.md):
+// 2 blocks of 256 threads per SM: dLk 19.6 -> 18.1 us, Br_Len_Opt 572 -> 537 us against 16 (then 4) blocks of 128.
+// PLK_REDUCE_BLOCKS_PER_SM / PLK_REDUCE_THREADS override them for A/B runs.
 int reduce_blocks_per_sm()
 {
   static const int v = [] {
     const char *e = getenv("PLK_REDUCE_BLOCKS_PER_SM");
-    const int   k = e ? atoi(e) : 4;
+    const int   k = e ? atoi(e) : 2;
     return k < 1 ? 1 : (k > 16 ? 16 : k);
   }();
   return v;
@@ -342,8 +344,8 @@ int reduce_threads_dna()
 {
   static const int v = [] {
     const char *e = getenv("PLK_REDUCE_THREADS");
-    const int   k = e ? atoi(e) : 128;
-    return (k == 256 || k == 512) ? k : 128;
+    const int   k = e ? atoi(e) : 256;
+    return (k == 128 || k == 512) ? k : 256;
   }();
   return v;
 }
@@ -353,10 +355,12 @@ int reduce_grid_dna(const plk_instance *inst)
   return std::max(1, std::min((groups + wpb - 1) / wpb, std::min(kMaxReduceBlocks, inst->num_sms * reduce_blocks_per_sm())));
 }
 
+// the generic (thread per pattern, 128-thread blocks) reduction kernels: 4 blocks per SM (2 is slower at 20 states)
 int reduce_grid(const plk_instance *inst, int threads)
 {
-  const int need = (inst->cfg.n_patterns + threads - 1) / threads;
-  return std::max(1, std::min(need, std::min(kMaxReduceBlocks, inst->num_sms * reduce_blocks_per_sm())));
+  static const int bps = getenv("PLK_REDUCE_BLOCKS_PER_SM") ? reduce_blocks_per_sm() : 4;
+  const int        need = (inst->cfg.n_patterns + threads - 1) / threads;
+  return std::max(1, std::min(need, std::min(kMaxReduceBlocks, inst->num_sms * bps)));
 }
 
 // where the reduction kernel about to be launched delivers its result
