@@ -128,6 +128,21 @@ def test_rooted_tree(tmp_path):
         assert abs(x - y) <= 1e-11 * abs(y), (x, y)
 
 
+@needs_bins
+def test_protein_search_through_the_binding(tmp_path):
+    """20 states end to end: LG + G4 on the amino-acid fixture (ambiguity codes B / Z / X included), SPR search with the
+    parsimony pre-filter on 20-bit state sets; final lnL and topology must equal the CPU run's."""
+    phy, nwk = stage(tmp_path, "synth_aa_small")
+    args = ["-i", phy, "-d", "aa", "-m", "LG", "-c", "4", "-a", "0.7", "-f", "m", "-o", "tlr", "-s", "SPR", "-b", "0",
+            "--r_seed", "1", "--no_memory_check"]
+    a, out = run(B200, str(tmp_path), args, {"PLK_SHIM_VERBOSE": "1"})
+    topo_a = _topology(str(tmp_path), phy)
+    b, _ = run(REF, str(tmp_path), args)
+    assert abs(a - b) <= 1e-5 * abs(b), (a, b)
+    assert topo_a == _topology(str(tmp_path), phy)
+    assert "ns=20" in out and re.search(r"phyml_b200: Pars (\d+)", out)
+
+
 def _numeric_rows(path):
     """every line of a PhyML text output as a list of tokens, numbers converted to float"""
     rows = []
