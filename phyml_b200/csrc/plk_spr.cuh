@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(kSprThreads)
       bool   oa, ob;
       if (cd.a.clv)
       {
-        const double4a v = ld256(cd.a.clv + off);
+        const double4a v = ldg256(cd.a.clv + off);
         oa = all_one(v);
         spr_matvec4(sP[0] + c * 16, v, ua);
         sx += cd.a.scale[site];
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(kSprThreads)
       }
       if (cd.b.clv)
       {
-        const double4a v = ld256(cd.b.clv + off);
+        const double4a v = ldg256(cd.b.clv + off);
         ob = all_one(v);
         spr_matvec4(sP[1] + c * 16, v, ub);
         sx += cd.b.scale[site];
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(kSprThreads)
       double pv[4];
       if (prune.clv)
       {
-        const double4a v = ld256(prune.clv + off);
+        const double4a v = ldg256(prune.clv + off);
         pv[0] = v.x, pv[1] = v.y, pv[2] = v.z, pv[3] = v.w;
       }
       else
@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(kSprThreads)
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb)
         {
-          const double4a q = ld256(cd.a.clv + off + kb * 32);
+          const double4a q = ldg256(cd.a.clv + off + kb * 32);
           v[kb * 4 + 0] = q.x, v[kb * 4 + 1] = q.y, v[kb * 4 + 2] = q.z, v[kb * 4 + 3] = q.w;
           oa = oa && all_one(q);
         }
@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(kSprThreads)
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb)
         {
-          const double4a q = ld256(cd.b.clv + off + kb * 32);
+          const double4a q = ldg256(cd.b.clv + off + kb * 32);
           v[kb * 4 + 0] = q.x, v[kb * 4 + 1] = q.y, v[kb * 4 + 2] = q.z, v[kb * 4 + 3] = q.w;
           ob = ob && all_one(q);
         }
@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(kSprThreads)
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb)
         {
-          const double4a q = ld256(prune.clv + off + kb * 32);
+          const double4a q = ldg256(prune.clv + off + kb * 32);
           pv[kb * 4 + 0] = q.x, pv[kb * 4 + 1] = q.y, pv[kb * 4 + 2] = q.z, pv[kb * 4 + 3] = q.w;
         }
       }
