@@ -254,7 +254,9 @@ int plk_pars_get_buffer(plk_instance *inst, int buf, int *ui, int *pars, int *p_
  * Post_Order_Pars / Pre_Order_Pars, src/pars.c:56-93) in ONE launch.  general != 0: the step-matrix branch. */
 int plk_pars_update(plk_instance *inst, int general, int n_ops, const plk_pars_op *ops);
 /* replaces the site loop of Pars (src/pars.c:40-48) + Pars_Core (src/pars.c:397-439) at the edge whose two
- * sides are `left` and `rght`: *c_pars = tree->c_pars (THIS instance's patterns), site_pars stays on the device. */
+ * sides are `left` and `rght`: *c_pars = tree->c_pars over this instance's patterns (the all-shard total on a
+ * plk_create_sharded instance; like lnL, the all-rank total once the instance is wired into a cross-GPU exchange);
+ * site_pars stays on the device. */
 int plk_pars_edge(plk_instance *inst, int general, int left, int rght, int *c_pars);
 /* the updates and the site loop in one launch: the whole of Pars(NULL) (n - 2 or 3n - 6 updates), or the one
  * update + Pars(b) of an SPR candidate scored by parsimony (src/spr.c:636-640). */
