@@ -631,11 +631,25 @@ def run_reference(args):
     # best case (2.2e8 updates/s; 3 000 columns per core drop to 1.6e8, memory-bandwidth bound)
     per_core = 1000 if w.ns == 4 else 200
     budget = int(1.5e7 * 90 / max(1, (args.steps + args.warmup)) / (w.n_taxa - 2))   # ~90 s at 1.5e7 updates/s/core
-    per_core = max(100, min(per_core, budget))
     total = w.block_sites * w.n_blocks
-    if per_core * cores > total:
-        per_core = max(50, total // cores)
-        cores = max(1, min(cores, total // per_core))
+    # when the WHOLE alignment of the workload fits the time budget and the host's memory (the reference's likelihood
+    # arena is (3n-2) x columns x ncatg x ns doubles per process), every core takes its share of ALL columns: the same
+    # alignment as the B200 arm, and the slices' lnL add up to the alignment's lnL
+    whole = total // cores if cores <= total else 0
+    arena = (3 * w.n_taxa - 2) * whole * 4 * w.ns * 8 * cores
+    try:
+        ram = os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES")
+    except (ValueError, OSError):
+        ram = 64 << 30
+    same_alignment = bool(w.n_blocks == 1 and whole >= 50 and whole <= budget and arena < 0.4 * ram
+                          and os.environ.get("PLK_REF_SAMPLE") is None)
+    if same_alignment:
+        per_core = whole
+    else:
+        per_core = max(100, min(per_core, budget))
+        if per_core * cores > total:
+            per_core = max(50, total // cores)
+            cores = max(1, min(cores, total // per_core))
     cb = cpu_baseline(name, cores=cores, sites=per_core * cores, evals=args.steps, warm=args.warmup)
     out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["s_per_eval"] * 1e3,
@@ -646,6 +660,16 @@ def run_reference(args):
                               "of the workload's alignment (its first columns, one slice per core)"},
            "cpu_baseline": cb,
            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if same_alignment:
+        out["config"]["note"] = ("reference CPU implementation (host cores); each step = one Lk(NULL) over the WHOLE alignment of "
+                                 "the workload, its columns split over one single-threaded process per core")
+        out["same_alignment"] = True
+        out["sites_evaluated"] = per_core * cores
+        out["evals_per_s"] = 1.0 / cb["s_per_eval"]
+        out["lnL"] = float(sum(cb.get("lnL_sample", [])))
+        pin = wl.load_pin(name)
+        if pin is not None and w.n_blocks == 1 and per_core * cores == total:
+            out["lnL_reference_single_process"] = float(pin["lnL"])
     print(json.dumps(out))
 
 

@@ -25,6 +25,10 @@ def test_reference_arm_prints_the_contract_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "reference" and cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"]
     assert "sample" in cb and d["vs_baseline"] is None and d["data"] == "synthetic" and d["dtype"] == "f64"
+    # a single-block workload that fits the budget is evaluated whole: the slices' lnL add up to the alignment's
+    if 4096 // (os.cpu_count() or 1) >= 50:
+        assert d.get("same_alignment") is True and d["sites_evaluated"] == 4096 // cb["cores"] * cb["cores"]
+        assert d["lnL"] < 0 and abs(d["lnL"] - sum(cb["lnL_sample"])) < 1e-9
 
 
 def test_reference_arm_is_silent_on_other_ranks():
