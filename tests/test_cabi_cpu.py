@@ -60,6 +60,23 @@ def test_shim_defines_every_re_bound_symbol():
         assert sym in text, sym
 
 
+def test_header_is_plain_c_and_cxx(tmp_path):
+    """the boundary is a C ABI: include/phyml_b200.h must compile on its own as C99 and as C++ (no torch / CUDA types)"""
+    import shutil
+    import subprocess
+
+    for cc, std, ext in (("gcc", "-std=c99", "c"), ("g++", "-std=c++11", "cpp")):
+        if not shutil.which(cc):
+            pytest.skip(f"{cc} not available")
+        src = tmp_path / f"t.{ext}"
+        src.write_text(f'#include "{HEADER}"\nint main(void) {{ plk_config c; plk_spr_cand s; plk_pars_op o; (void)c; (void)s; (void)o; '
+                       "return sizeof(plk_op) == 28 ? 0 : 1; }\n")
+        res = subprocess.run([cc, std, "-Wall", "-Werror", "-pedantic", "-fsyntax-only", str(src)], capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr
+    includes = re.findall(r"#include\s*[<\"]([^>\"]+)[>\"]", open(HEADER).read())
+    assert sorted(includes) == ["stddef.h", "stdint.h"], includes
+
+
 def test_no_cpu_fallback():
     """Without a CUDA device plk_create must fail with PLK_ERR_CUDA and say why (never compute on the CPU)."""
     import torch
