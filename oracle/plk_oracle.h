@@ -6,8 +6,10 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline leg may load it.  The product
  * (phyml_b200/) never links, imports or calls anything in this directory.
  *
- * Parity pinning: tests/test_oracle_golden.py checks every function below against arrays
- * dumped from the unmodified reference (oracle/ref_driver.c -> tests/golden/*.npz).
+ * Parity pinning: tests/test_oracle_golden.py checks every likelihood function below against arrays
+ * dumped from the unmodified reference (oracle/ref_driver.c --dump -> tests/golden/NAME.npz), and
+ * tests/test_pars_cpu.py the parsimony functions against the reference's Pars / Update_Partial_Pars
+ * state (oracle/ref_driver.c --dump_pars -> tests/golden/pars/NAME.npz).
  *
  * Layouts:  CLV  [site][catg][state]      tip vector [site][state] (0/1 doubles)
  *           P    [catg][from][to]         scalers    int[site]
