@@ -357,6 +357,8 @@ def measured_traffic(name, timeout=240):
     ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
     if not os.path.exists(ncu):
         return None, "ncu not found"
+    if os.environ.get("CUDA_INJECTION64_PATH") or any(k.startswith("NV_NSIGHT") for k in os.environ):
+        return None, "already running under a profiler"
     cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "--print-units", "base",
            "-k", "regex:k_traverse", "-s", "3", "-c", "1", "--csv", sys.executable, os.path.abspath(__file__),
            "--steps", "1", "--warmup", "3", "--no-cpu-baseline", "--no-secondary", "--no-traffic", "--workload", name]

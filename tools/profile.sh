@@ -7,7 +7,7 @@ TAG=${1:-r1}
 WL=${2:-dna_100x100k}
 OUT=gpurun_out
 mkdir -p $OUT
-CMD="timeout 240 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-secondary --workload $WL"
+CMD="timeout 240 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-secondary --no-traffic --workload $WL"
 # every launch with its device time (cold-cache, serialised: compare SHARES, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_${TAG}_${WL}.csv $CMD > $OUT/ncu_list_${TAG}_${WL}.log 2>&1
 # full captures
