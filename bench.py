@@ -348,7 +348,7 @@ def roofline_of(rec, peaks):
     return out
 
 
-def measured_traffic(name, timeout=240):
+def measured_traffic(name, timeout=120):
     """DRAM bytes (read + write) of ONE launch of the traversal kernel, measured now: this same script re-run for one
     step under `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` (warm launch: 3 skipped).  Only the byte counters
     are taken from the profiled run -- never a time.  Returns (bytes, source) or (None, why)."""
